@@ -1,0 +1,42 @@
+"""CPU: the C++ oracle against the golden vectors written by tests/golden/gen_golden.py (an
+independent numpy/scipy restatement).  PARITY UNPINNED vs LApx itself — see oracle header."""
+import numpy as np
+import pytest
+
+from common import load_golden, rel_err, run_golden_schedule, solver_from_golden
+from lapx_b200 import api
+
+CASES = ["fcc8_strain", "fcc_12x10x8_tension", "hcp8_compression"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_numpy_golden(name, oracle_lib, product_lib):
+    g = load_golden(name)
+    s = solver_from_golden(oracle_lib, product_lib, g)
+    seen = {}
+
+    def hook(s, inc, it, where):
+        if inc == 0 and it == 1 and where == "green":
+            seen["e_after_green_inc0_it2"] = s.get_field(api.FIELD_STRAIN)
+            seen["de_inc0_it2"] = s.get_field(api.FIELD_STRAIN_INCR)
+        if inc == 0 and it == 1 and where == "const":
+            seen["sig_inc0_it2"] = s.get_field(api.FIELD_STRESS)
+        if where == "end":
+            seen[f"sig_end_inc{inc}"] = s.get_field(api.FIELD_STRESS)
+            seen[f"e_end_inc{inc}"] = s.get_field(api.FIELD_STRAIN)
+            seen[f"epsp_end_inc{inc}"] = s.get_field(api.FIELD_PLASTIC_STRAIN)
+            seen[f"crss_end_inc{inc}"] = s.get_field(api.FIELD_CRSS)
+
+    rows = run_golden_schedule(s, g, hook)
+    ref = g["reports"]
+    assert rows.shape == ref.shape
+    # iteration bookkeeping identical, Newton counts identical
+    assert np.array_equal(rows[:, :2], ref[:, :2])
+    assert np.array_equal(rows[:, 16], ref[:, 16])
+    # error norms and macro values: fp64 rounding only (tolerance 1e-8 relative, BASELINE.json north_star)
+    assert rel_err(rows[:, 2:16], ref[:, 2:16]) < 1e-8
+    for k, v in seen.items():
+        assert rel_err(v, g[k]) < 1e-8, k
+    # reference medium computed by the oracle's own Voigt average equals the stored one
+    s2 = solver_from_golden(oracle_lib, product_lib, g, c0=None)
+    assert rel_err(s2.get_reference_medium(), g["c0_voigt"]) < 1e-12
