@@ -1,0 +1,508 @@
+// evp_core.h — thread-level math of the CUDA kernels, written as __host__ __device__ inline
+// functions so that tests/emu can run exactly the same arithmetic on the CPU (no GPU in the
+// build container).  Nothing in here is a CPU fallback: the product library only calls these
+// from __global__ kernels (kernels.cu).
+//
+// Units implemented:  a1/a3 Stockham radix passes, a2 Green-operator point
+// function, a4 crystal-frame Newton solve, a5 multiplier identity, a6 norm contributions.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/evpfft.h"
+
+#if defined(__CUDACC__)
+#define EVP_HD __host__ __device__ __forceinline__
+#else
+#define EVP_HD inline
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace evp {
+
+constexpr double kRSQ2 = 0.70710678118654752440;   // 1/sqrt(2)
+constexpr double kSQ2 = 1.41421356237309504880;
+constexpr double kRSQ3 = 0.57735026918962576451;
+constexpr double kRSQ6 = 0.40824829046386301637;
+
+// ---------------------------------------------------------------------------------------------
+// symmetric-tensor bases.  Cartesian order 11,22,33,23,13,12.  b-basis (Lebensohn):
+//   b0=(22-11)/sqrt2  b1=(2*33-11-22)/sqrt6  b2=sqrt2*23  b3=sqrt2*13  b4=sqrt2*12  b5=tr/sqrt3
+// ---------------------------------------------------------------------------------------------
+EVP_HD void cart_to_b(const double c[6], double b[6]) {
+  b[0] = (c[1] - c[0]) * kRSQ2;
+  b[1] = (2.0 * c[2] - c[0] - c[1]) * kRSQ6;
+  b[2] = kSQ2 * c[3];
+  b[3] = kSQ2 * c[4];
+  b[4] = kSQ2 * c[5];
+  b[5] = (c[0] + c[1] + c[2]) * kRSQ3;
+}
+EVP_HD void b_to_cart(const double b[6], double c[6]) {
+  const double h = b[5] * kRSQ3, d1 = b[1] * kRSQ6, d0 = b[0] * kRSQ2;
+  c[0] = h - d1 - d0;
+  c[1] = h - d1 + d0;
+  c[2] = h + 2.0 * d1;
+  c[3] = b[2] * kRSQ2;
+  c[4] = b[3] * kRSQ2;
+  c[5] = b[4] * kRSQ2;
+}
+
+// packed upper triangle of a symmetric 6x6: row i starts at i*6 - i(i-1)/2
+EVP_HD constexpr int sidx(int i, int j) { return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j)); }
+
+// 5x5 rotation of deviatoric b-vectors: a_sample = M a_crystal, a_crystal = M^T a_sample,
+// M[al*5+be] = b^al : (R b^be R^T), R = crystal->sample, row major.  The 6th (hydrostatic)
+// component is invariant.
+EVP_HD void rot_b5(const double R[9], double M[25]) {
+  // symmetric outer products of the columns r_k of R:  O^{kl}_c, c in Cartesian 6-order
+  double O[6][6];  // [pair kl in order 00,11,22,12,02,01][cart comp]
+  const int ck[6] = {0, 1, 2, 1, 0, 0}, cl[6] = {0, 1, 2, 2, 2, 1};
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    const int k = ck[p], l = cl[p];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const int i = ck[c], j = cl[c];
+      O[p][c] = 0.5 * (R[3 * i + k] * R[3 * j + l] + R[3 * i + l] * R[3 * j + k]);
+    }
+  }
+  double t[6], tb[6];
+  // b0 -> (O11 - O00)/sqrt2
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t[c] = (O[1][c] - O[0][c]) * kRSQ2;
+  cart_to_b(t, tb);
+#pragma unroll
+  for (int a = 0; a < 5; ++a) M[a * 5 + 0] = tb[a];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t[c] = (2.0 * O[2][c] - O[0][c] - O[1][c]) * kRSQ6;
+  cart_to_b(t, tb);
+#pragma unroll
+  for (int a = 0; a < 5; ++a) M[a * 5 + 1] = tb[a];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {  // b2 <- sqrt2*O12, b3 <- sqrt2*O02, b4 <- sqrt2*O01
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t[c] = kSQ2 * O[3 + q][c];
+    cart_to_b(t, tb);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) M[a * 5 + 2 + q] = tb[a];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-phase constant tables used by the constitutive kernel (crystal frame, b-basis)
+// ---------------------------------------------------------------------------------------------
+struct PhaseDev {
+  int32_t nsys;
+  int32_t nmodes;
+  double Sc[21];                  // crystal compliance, packed
+  double m[EVP_MAX_SYS][5];       // Schmid tensors (deviatoric b components)
+  double mm[EVP_MAX_SYS][15];     // m (x) m, packed upper triangle of the 5x5 block
+  double g0[EVP_MAX_SYS];
+  double nrate[EVP_MAX_SYS];
+  int32_t npow[EVP_MAX_SYS];      // n-1 when n is an integer in [1,64], else -1 -> pow()
+  int32_t twin[EVP_MAX_SYS];
+  int32_t mode[EVP_MAX_SYS];
+  double alpha[EVP_MAX_SYS][3];   // skew part of b(x)n, axial (32,13,21), crystal frame
+  // hardening (commit kernel)
+  double tau0[EVP_MAX_MODES], tau1[EVP_MAX_MODES], theta0[EVP_MAX_MODES], theta1[EVP_MAX_MODES];
+  double hlat[EVP_MAX_MODES][EVP_MAX_MODES];
+};
+
+EVP_HD constexpr int s5idx(int i, int j) { return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j)); }
+
+// x^(n-1) for the power law; integer exponents by binary powering (same tree as the oracle's
+// x^(n-1); the oracle multiplies the same sequence).
+EVP_HD double pow_nm1(double x, int npow, double nrate) {
+  if (npow >= 0) {
+    double r = 1.0, b = x;
+    int k = npow;
+    while (k) {
+      if (k & 1) r *= b;
+      b *= b;
+      k >>= 1;
+    }
+    return r;
+  }
+  return pow(x, nrate - 1.0);
+}
+
+// shear rate and tangent of one system at resolved shear stress tau, itc = 1/tau_c
+EVP_HD void slip_rate(const PhaseDev &P, int s, double tau, double itc, double &gd, double &dgd) {
+  const double x = fabs(tau) * itc;
+  const double xn1 = pow_nm1(x, P.npow[s], P.nrate[s]);
+  const bool off = (P.twin[s] != 0) && (tau <= 0.0);
+  const double g = off ? 0.0 : P.g0[s] * xn1;
+  gd = g * x * (tau >= 0.0 ? 1.0 : -1.0);
+  dgd = g * P.nrate[s] * itc;
+}
+
+// in-place LDL^T of a packed symmetric 6x6 and solve; returns false on a non-positive pivot
+EVP_HD bool ldl6_solve(double a[21], double b[6]) {
+  double invd[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double w[6];
+    double d = a[sidx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      w[k] = a[sidx(k, j)] * a[sidx(k, k)];
+      d -= a[sidx(k, j)] * w[k];
+    }
+    a[sidx(j, j)] = d;
+    ok = ok && (d > 0.0);
+    const double inv = 1.0 / d;
+    invd[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = a[sidx(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= a[sidx(k, i)] * w[k];
+      a[sidx(j, i)] = t * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) b[i] -= a[sidx(k, i)] * b[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[i] *= invd[i];
+#pragma unroll
+  for (int i = 4; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) b[i] -= a[sidx(i, k)] * b[k];
+  }
+  return ok;
+}
+
+// Row a4: Newton solve of  Jb*s + dt*edp(s) = g  in the crystal frame (b-basis).
+//   Jb = S0_c + S_c (packed), g = S0:sig_old + e - eps_p (rotated to the crystal frame)
+//   s: in = initial guess (sig_old), out = solution.  ITC(s) returns 1/tau_c of system s.
+// Returns the number of Newton updates; *bad is set when a non-finite value / bad pivot shows up.
+template <class ITC>
+EVP_HD int newton_crystal(const PhaseDev &P, const double Jb[21], const double g[6], double s[6], double dt,
+                          double tol, int itmax, ITC itc, int *bad) {
+  int it = 0;
+  while (it < itmax) {
+    double J[21], F[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) J[k] = Jb[k];
+    // F = g - Jb*s - dt*edp   (right-hand side of J*delta = F)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double acc = g[i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc -= Jb[sidx(i, j)] * s[j];
+      F[i] = acc;
+    }
+    const int ns = P.nsys;
+    for (int q = 0; q < ns; ++q) {
+      double tau = 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tau += P.m[q][c] * s[c];
+      double gd, dgd;
+      slip_rate(P, q, tau, itc(q), gd, dgd);
+      const double a = dt * gd, bcoef = dt * dgd;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) F[c] -= a * P.m[q][c];
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = i; j < 5; ++j) J[sidx(i, j)] += bcoef * P.mm[q][s5idx(i, j)];
+    }
+    const bool ok = ldl6_solve(J, F);
+    double dn = 0.0, sn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      s[i] += F[i];
+      dn += F[i] * F[i];
+      sn += s[i] * s[i];
+    }
+    ++it;
+    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
+    if (dn <= tol * tol * sn) break;
+  }
+  return it;
+}
+
+
+// kernel-constant parameters of the constitutive kernel
+struct ConstParams {
+  double S0b[21];           // reference compliance, b-basis, packed (sample frame)
+  double dt, tol_newton;
+  int newton_itmax, iso_c0;
+};
+
+// rotate the packed reference compliance into the crystal frame: S0c = Q^T S0b Q, Q = diag(M, 1)
+EVP_HD void rotate_s0(const double *S0b, const double M[25], double out[21]) {
+#pragma unroll
+  for (int be = 0; be < 6; ++be) {
+    double T[6];  // T[ga] = sum_de S0b[ga][de] Q[de][be]
+#pragma unroll
+    for (int ga = 0; ga < 6; ++ga) {
+      if (be == 5) {
+        T[ga] = S0b[sidx(ga, 5)];
+      } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int de = 0; de < 5; ++de) acc += S0b[sidx(ga, de)] * M[de * 5 + be];
+        T[ga] = acc;
+      }
+    }
+#pragma unroll
+    for (int al = 0; al <= be; ++al) {
+      if (al == 5) {
+        out[sidx(5, 5)] = T[5];
+      } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int ga = 0; ga < 5; ++ga) acc += M[ga * 5 + al] * T[ga];
+        out[sidx(al, be)] = acc;
+      }
+    }
+  }
+}
+
+// Rows a4+a5+a6 for one voxel.  sig: in = sigma_old (Cartesian 6), out = sigma_new.
+// em = e - eps_p (Cartesian 6).  ITC: accessor of 1/tau_c per system.
+// Outputs: *ds = |sig_new - sig_old|, *de = |S0:(sig_new - sig_old)|, returns Newton iterations.
+template <class ITC>
+EVP_HD int constitutive_voxel(const PhaseDev &P, const ConstParams &cp, const double R[9], double sig[6], const double em[6],
+                              ITC itc, double *ds, double *de, int *bad) {
+  double M[25];
+  rot_b5(R, M);
+  double so[6], eb[6];
+  cart_to_b(sig, so);
+  cart_to_b(em, eb);
+  // g = S0:sig_old + e - eps_p   (sample frame)
+  double g[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double acc = eb[i];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc += cp.S0b[sidx(i, j)] * so[j];
+    g[i] = acc;
+  }
+  // to the crystal frame: a_c = M^T a_s on the deviatoric part
+  double gc[6], sc[6], s0c[6];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double x = 0.0, y = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      x += M[b * 5 + a] * g[b];
+      y += M[b * 5 + a] * so[b];
+    }
+    gc[a] = x;
+    sc[a] = y;
+  }
+  gc[5] = g[5];
+  sc[5] = so[5];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) s0c[a] = sc[a];
+  double Jb[21];
+  if (cp.iso_c0) {
+#pragma unroll
+    for (int k = 0; k < 21; ++k) Jb[k] = cp.S0b[k];
+  } else {
+    rotate_s0(cp.S0b, M, Jb);
+  }
+#pragma unroll
+  for (int k = 0; k < 21; ++k) Jb[k] += P.Sc[k];
+  const int nit = newton_crystal(P, Jb, gc, sc, cp.dt, cp.tol_newton, cp.newton_itmax, itc, bad);
+  // norms (row a6): |dsig| and |S0:dsig| = |(Jb - Sc) dsig|, both rotation invariant
+  double d[6], ds2 = 0.0, de2 = 0.0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    d[a] = sc[a] - s0c[a];
+    ds2 += d[a] * d[a];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc += (Jb[sidx(i, j)] - P.Sc[sidx(i, j)]) * d[j];
+    de2 += acc * acc;
+  }
+  *ds = sqrt(ds2);
+  *de = sqrt(de2);
+  // back to the sample frame; row a5: lambda_new == sigma_new, one stored field
+  double sb[6];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double x = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) x += M[a * 5 + b] * sc[b];
+    sb[a] = x;
+  }
+  sb[5] = sc[5];
+  b_to_cart(sb, sig);
+  return nit;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row a2: Green operator at one frequency (vector form):
+//   A_ik = C0_ijkl xi_j xi_l, G = A^-1, t = lam.xi, u = G t, de_ij = (u_i xi_j + u_j xi_i)/2
+// KA[ik(6)][6]: host-precomputed coefficients so that A_ik = sum_m KA[ik][m] * p_m with
+// p = (xx, yy, zz, yz, xz, xy) products of xi.  SC[36]: S0 acting on Cartesian 6-vectors
+// (Nyquist planes).  `scale` = 1/(nx ny nz) folds the inverse-FFT normalisation in.
+// ---------------------------------------------------------------------------------------------
+struct GreenConst {
+  double KA[6][6];
+  double SC[36];
+};
+
+EVP_HD void green_point(const GreenConst &G0, double x, double y, double z, bool zero, bool nyq, double scale,
+                        const double2 lam[6], double2 out[6]) {
+  if (zero) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[c] = make_double2(0.0, 0.0);
+    return;
+  }
+  if (nyq) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        re += G0.SC[6 * a + b] * lam[b].x;
+        im += G0.SC[6 * a + b] * lam[b].y;
+      }
+      out[a] = make_double2(re * scale, im * scale);
+    }
+    return;
+  }
+  const double p[6] = {x * x, y * y, z * z, y * z, x * z, x * y};
+  double A[6];  // 00,11,22,12,02,01
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) acc += G0.KA[q][m] * p[m];
+    A[q] = acc;
+  }
+  // inverse of the symmetric 3x3 [A0 A5 A4; A5 A1 A3; A4 A3 A2]
+  const double c00 = A[1] * A[2] - A[3] * A[3];
+  const double c01 = A[4] * A[3] - A[5] * A[2];
+  const double c02 = A[5] * A[3] - A[4] * A[1];
+  const double c11 = A[0] * A[2] - A[4] * A[4];
+  const double c12 = A[5] * A[4] - A[0] * A[3];
+  const double c22 = A[0] * A[1] - A[5] * A[5];
+  const double det = A[0] * c00 + A[5] * c01 + A[4] * c02;
+  const double id = scale / det;
+  const double g00 = c00 * id, g01 = c01 * id, g02 = c02 * id, g11 = c11 * id, g12 = c12 * id, g22 = c22 * id;
+  // t_k = lam_kl xi_l   (lam order 11,22,33,23,13,12)
+  const double t0r = lam[0].x * x + lam[5].x * y + lam[4].x * z, t0i = lam[0].y * x + lam[5].y * y + lam[4].y * z;
+  const double t1r = lam[5].x * x + lam[1].x * y + lam[3].x * z, t1i = lam[5].y * x + lam[1].y * y + lam[3].y * z;
+  const double t2r = lam[4].x * x + lam[3].x * y + lam[2].x * z, t2i = lam[4].y * x + lam[3].y * y + lam[2].y * z;
+  const double u0r = g00 * t0r + g01 * t1r + g02 * t2r, u0i = g00 * t0i + g01 * t1i + g02 * t2i;
+  const double u1r = g01 * t0r + g11 * t1r + g12 * t2r, u1i = g01 * t0i + g11 * t1i + g12 * t2i;
+  const double u2r = g02 * t0r + g12 * t1r + g22 * t2r, u2i = g02 * t0i + g12 * t1i + g22 * t2i;
+  out[0] = make_double2(u0r * x, u0i * x);
+  out[1] = make_double2(u1r * y, u1i * y);
+  out[2] = make_double2(u2r * z, u2i * z);
+  out[3] = make_double2(0.5 * (u1r * z + u2r * y), 0.5 * (u1i * z + u2i * y));
+  out[4] = make_double2(0.5 * (u0r * z + u2r * x), 0.5 * (u0i * z + u2i * x));
+  out[5] = make_double2(0.5 * (u0r * y + u1r * x), 0.5 * (u0i * y + u1i * x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rows a1/a3: Stockham autosort radix passes.  A block owns L lines of length N in shared memory;
+// thread (l, q), q in [0, N/8), owns the 8 points q + m*N/8 of line l in every pass.
+// ---------------------------------------------------------------------------------------------
+EVP_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+EVP_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+EVP_HD double2 cmul(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+EVP_HD double2 cmulc(double2 a, double2 w) { return make_double2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }  // a*conj(w)
+template <bool INV>
+EVP_HD double2 mul_mi(double2 a) {  // forward: a * (-i);  inverse: a * (+i)
+  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+template <bool INV>
+EVP_HD void bfly2(double2 *v) {
+  const double2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <bool INV>
+EVP_HD void bfly4(double2 *v) {
+  const double2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+  const double2 t2 = cadd(v[1], v[3]), t3 = mul_mi<INV>(csub(v[1], v[3]));
+  v[0] = cadd(t0, t2);
+  v[2] = csub(t0, t2);
+  v[1] = cadd(t1, t3);
+  v[3] = csub(t1, t3);
+}
+template <bool INV>
+EVP_HD void bfly8(double2 *v) {
+  // radix-2 DIF stage, then two radix-4
+  double2 a[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = cadd(v[i], v[i + 4]);
+    b[i] = csub(v[i], v[i + 4]);
+  }
+  // b[i] *= W8^i  (forward W8 = exp(-i pi/4))
+  {
+    const double2 t = b[1];
+    b[1] = INV ? make_double2((t.x - t.y) * kRSQ2, (t.x + t.y) * kRSQ2) : make_double2((t.x + t.y) * kRSQ2, (t.y - t.x) * kRSQ2);
+    b[2] = mul_mi<INV>(b[2]);
+    const double2 u = b[3];
+    b[3] = INV ? make_double2((-u.x - u.y) * kRSQ2, (u.x - u.y) * kRSQ2) : make_double2((u.y - u.x) * kRSQ2, (-u.x - u.y) * kRSQ2);
+  }
+  bfly4<INV>(a);
+  bfly4<INV>(b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = a[i];
+    v[2 * i + 1] = b[i];
+  }
+}
+template <int R, bool INV>
+EVP_HD void bfly(double2 *v) {
+  if (R == 2) bfly2<INV>(v);
+  else if (R == 4) bfly4<INV>(v);
+  else bfly8<INV>(v);
+}
+
+// first-pass radix for length N = 2^k >= 8 so that the remaining passes are all radix 8
+EVP_HD constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+EVP_HD constexpr int first_radix(int n) { return (ilog2(n) % 3 == 0) ? 8 : (ilog2(n) % 3 == 1 ? 2 : 4); }
+
+// load the thread's 8 points for a pass of radix R:  butterfly b handles j = q + b*N/8,
+// inputs i = j + r*N/R.  OFF(i) maps a line index to the shared-memory element offset.
+template <int N, int R, class OFF>
+EVP_HD void pass_load(const double2 *s, int q, double2 v[8], OFF off) {
+#pragma unroll
+  for (int b = 0; b < 8 / R; ++b) {
+    const int j = q + b * (N / 8);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b * R + r] = s[off(j + r * (N / R))];
+  }
+}
+// twiddle + butterfly + autosort store.  tw[k] = exp(-2 pi i k / N).
+template <int N, int R, int NS, bool INV, class OFF, class TW>
+EVP_HD void pass_store(double2 *s, int q, double2 v[8], OFF off, TW tw) {
+#pragma unroll
+  for (int b = 0; b < 8 / R; ++b) {
+    const int j = q + b * (N / 8);
+    const int k = j % NS;
+    if (NS > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        const double2 w = tw(r * k * (N / (NS * R)));
+        v[b * R + r] = INV ? cmulc(v[b * R + r], w) : cmul(v[b * R + r], w);
+      }
+    }
+    bfly<R, INV>(&v[b * R]);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[off(base + r * NS)] = v[b * R + r];
+  }
+}
+
+}  // namespace evp

@@ -1,0 +1,75 @@
+// kernels.cuh — hand-written sm_100a kernels of the EVPFFT equilibrium iteration.
+//   K2 k_xfwd        a1  x pass: two real fields -> two half spectra (two-for-one complex FFT)
+//   K3 k_ypass<fwd>  a1  y pass on tiles of 8 kx-columns
+//   K4 k_zfused      a1+a2+a3  z forward FFT, Green operator per frequency, z inverse FFT
+//   K5 k_ypass<inv>  a3
+//   K6 k_xinv        a3  x inverse pass fused with  e <- e - de + dE
+//   K1 k_constitutive a4+a5+a6  crystal-frame Newton, norms by warp shuffles
+//      k_reduce / k_macro   a6 second stage + a7 on the device
+//      k_commit      §8(f).1 per-increment state update (plastic strain, Voce hardening)
+// Reference counterpart: absent (mount holds only LICENSE); units per SURVEY.md §8(a).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "evp_core.h"
+
+namespace evp {
+
+// ---------------------------------------------------------------------------------------------
+// spectral buffer addressing.  One formula serves the plain local layout, the all-to-all "send"
+// layout (rows grouped by destination rank) and the "recv" layout (planes grouped by source).
+//   y-split view : addr(c, zl, y)   = (y / nyl) * dstride + c * cstride + zl * zstride + (y % nyl) * nxp
+//   z-split view : addr(c, z, yl)   = (z / nzl) * dstride + c * cstride + (z % nzl) * zstride + yl * nxp
+// with cstride = nzl*nyl*nxp, zstride = nyl*nxp, dstride = 6*cstride.  Single GPU: nyl = ny, nzl = nz.
+// ---------------------------------------------------------------------------------------------
+struct SpecLayout {
+  int nyl, nzl, nxp, nxh;
+  long long cstride, zstride, dstride;
+  __host__ __device__ long long row_ysplit(int c, int zl, int y) const {
+    return (long long)(y / nyl) * dstride + (long long)c * cstride + (long long)zl * zstride + (long long)(y % nyl) * nxp;
+  }
+  __host__ __device__ long long row_zsplit(int c, int z, int yl) const {
+    return (long long)(z / nzl) * dstride + (long long)c * cstride + (long long)(z % nzl) * zstride + (long long)yl * nxp;
+  }
+};
+
+// device-resident macroscopic state (rows a6/a7); one copy per handle
+struct MacroDev {
+  double E[6], Et[6], dEpend[6], savg[6], scau[6];
+  double Mmac[36];          // dE = Mmac (scau - savg): (C0_TT)^-1 embedded, zero rows for strain control
+  double err_s, err_e, newton_mean;
+  double epavg[6];
+  int newton_max, nonfinite, iter, pad;
+};
+
+struct Fields {
+  double *sig, *e, *epsp, *edotp, *crss, *rot, *gacc, *twinf, *de;
+  int32_t *grain, *phase;
+  long long N;              // local voxels; component stride of every SoA field
+};
+
+constexpr int kPartial = 16;  // doubles per block partial: ds, de, sig[6], nit_sum, nit_max, bad, epsp[6]->(commit reuses 2..7)
+
+void upload_phase_tables(const PhaseDev *ph, int nph);
+void upload_green(const GreenConst &g);
+void upload_const_params(const ConstParams &p);
+
+// launches (all on `st`)
+void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int nrows, SpecLayout L, const double2 *tw, cudaStream_t st);
+void launch_ypass(int ny, bool inv, const double2 *in, double2 *out, SpecLayout Lin, SpecLayout Lout, int nzl, const double2 *tw,
+                  cudaStream_t st);
+void launch_zfused(int nz, bool fwd_only, double2 *Wt, SpecLayout L, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz,
+                   const double2 *tw, cudaStream_t st);
+void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int nrows, SpecLayout L,
+                 const double2 *tw, cudaStream_t st);
+void launch_constitutive(const Fields &f, int nsmax, double *partials, int *nblocks_out, cudaStream_t st);
+void launch_reduce(const double *partials, int nblocks, double *totals, cudaStream_t st);
+void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
+void launch_commit(const Fields &f, int nsmax, double dt, double *partials, int *nblocks_out, cudaStream_t st);
+void launch_fill(double *p, long long n, double v, cudaStream_t st);
+void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st);
+bool fft_size_supported(int n);
+int constitutive_block();
+
+}  // namespace evp

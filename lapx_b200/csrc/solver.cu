@@ -1,0 +1,764 @@
+// solver.cu — host side of the product library: the C ABI of include/evpfft.h on top of the
+// sm_100a kernels (kernels.cu).  There is NO CPU fallback here: without an sm_100 device
+// evp_create fails with EVP_ERR_DEVICE.
+// Reference counterpart: absent (/root/reference holds only LICENSE); ABI per SURVEY.md §8(b).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "host_math.h"
+
+using namespace evp;
+using namespace evp::host;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- NCCL through dlopen (torch's bundled libnccl.so.2 if the process already loaded it) ----
+struct Id128 { char b[128]; };
+struct Nccl {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+bool load_nccl(std::string *err) {
+  if (g_nccl.lib) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) { *err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+  auto sym = [&](const char *s) { return dlsym(lib, s); };
+  g_nccl.GetUniqueId = (int (*)(void *))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+  g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))sym("ncclSend");
+  g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))sym("ncclRecv");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+  g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.AllReduce) {
+    *err = "libnccl lacks required symbols";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2, kNcclChar = 0;  // ncclFloat64, ncclSum, ncclMax, ncclInt8
+
+}  // namespace
+
+struct evp_solver {
+  evp_grid g{};
+  int nx = 0, ny = 0, nz = 0, nxh = 0, nxp = 0;
+  int nranks = 1, rank = 0, device = 0;
+  int nzl = 0, z0 = 0, nyl = 0, ky0 = 0;
+  long long N = 0;        // local voxels
+  double Ntot = 0;        // global voxels
+  int nphases = 0, nsmax = 0;
+  std::vector<evp_phase> ph;
+  std::vector<PhaseDev> phd;
+  cudaStream_t st = nullptr;
+  Fields f{};
+  double2 *WA = nullptr, *WB = nullptr;
+  double2 *twx = nullptr, *twy = nullptr, *twz = nullptr;
+  MacroDev *d_macro = nullptr, *h_macro = nullptr;  // h_macro pinned
+  double *d_partials = nullptr, *d_totals = nullptr;
+  int nblocks = 0;
+  SpecLayout Lplain{}, Lsplit{};
+  double C0m[36]{}, S0m[36]{};
+  ConstParams cp{};
+  GreenConst green{};
+  bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
+  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-9, 100};
+  int iudot[9]{}, iscau[6]{};
+  double udot[9]{}, scau[6]{};
+  bool strain_ctl[6]{};
+  double Et[6]{}, Edot_prev[6]{};
+  double dt = 0;
+  int flags = 0;  // bit0: kernel timing, bit1: keep strain increment
+  cudaEvent_t ev[10]{};
+  bool ev_made = false;
+  double last_ms[8]{};
+  void *comm = nullptr;
+  std::string err;
+};
+
+namespace {
+
+int fail(evp_handle h, int code, const std::string &m) {
+  if (h) h->err = m; else g_create_error = m;
+  return code;
+}
+#define CUDA_OK(h, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(h, EVP_ERR_DEVICE, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+double2 *make_twiddles(int n) {
+  std::vector<double2> t(n);
+  for (int k = 0; k < n; ++k) {
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+    t[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  double2 *d = nullptr;
+  if (cudaMalloc(&d, sizeof(double2) * n) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, t.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+  return d;
+}
+
+size_t field_comps(const evp_solver *S, int f) {
+  switch (f) {
+    case EVP_FIELD_STRESS: case EVP_FIELD_STRAIN: case EVP_FIELD_PLASTIC_STRAIN:
+    case EVP_FIELD_PLASTIC_RATE: case EVP_FIELD_STRAIN_INCR: return 6;
+    case EVP_FIELD_CRSS: case EVP_FIELD_TWIN_FRACTION: return (size_t)S->nsmax;
+    case EVP_FIELD_ROTATION: return 9;
+    case EVP_FIELD_GRAIN: case EVP_FIELD_PHASE: case EVP_FIELD_GAMMA_ACC: return 1;
+    default: return 0;
+  }
+}
+void *field_ptr(evp_solver *S, int f, size_t *el) {
+  *el = sizeof(double);
+  switch (f) {
+    case EVP_FIELD_STRESS: return S->f.sig;
+    case EVP_FIELD_STRAIN: return S->f.e;
+    case EVP_FIELD_PLASTIC_STRAIN: return S->f.epsp;
+    case EVP_FIELD_PLASTIC_RATE: return S->f.edotp;
+    case EVP_FIELD_CRSS: return S->f.crss;
+    case EVP_FIELD_ROTATION: return S->f.rot;
+    case EVP_FIELD_GAMMA_ACC: return S->f.gacc;
+    case EVP_FIELD_TWIN_FRACTION: return S->f.twinf;
+    case EVP_FIELD_STRAIN_INCR: return S->f.de;
+    case EVP_FIELD_GRAIN: *el = sizeof(int32_t); return S->f.grain;
+    case EVP_FIELD_PHASE: *el = sizeof(int32_t); return S->f.phase;
+    default: return nullptr;
+  }
+}
+
+int nccl_check(evp_handle h, int rc, const char *what) {
+  if (rc == 0) return EVP_OK;
+  return fail(h, EVP_ERR_DEVICE, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"));
+}
+
+// all-to-all of equal contiguous chunks (FFT transpose): grouped ncclSend/ncclRecv
+int all_to_all(evp_handle h, const double2 *send, double2 *recv) {
+  const size_t chunk = (size_t)h->Lsplit.dstride * sizeof(double2);
+  int rc = g_nccl.GroupStart();
+  for (int p = 0; p < h->nranks && rc == 0; ++p) {
+    rc = g_nccl.Send((const char *)send + (size_t)p * chunk, chunk, kNcclChar, p, h->comm, h->st);
+    if (rc == 0) rc = g_nccl.Recv((char *)recv + (size_t)p * chunk, chunk, kNcclChar, p, h->comm, h->st);
+  }
+  const int rc2 = g_nccl.GroupEnd();
+  return nccl_check(h, rc ? rc : rc2, "nccl all-to-all");
+}
+
+void rec(evp_handle h, int i) {
+  if ((h->flags & 1) && h->ev_made) cudaEventRecord(h->ev[i], h->st);
+}
+
+// rows a1+a2+a3
+int enqueue_green(evp_handle h) {
+  const int nrows = h->ny * h->nzl;
+  rec(h, 0);
+  launch_xfwd(h->nx, h->f.sig, h->WB, h->N, nrows, h->Lplain, h->twx, h->st);
+  rec(h, 1);
+  launch_ypass(h->ny, false, h->WB, h->WA, h->Lplain, h->Lsplit, h->nzl, h->twy, h->st);
+  rec(h, 2);
+  double2 *Wz = h->WA;
+  if (h->nranks > 1) {
+    int rc = all_to_all(h, h->WA, h->WB);
+    if (rc) return rc;
+    Wz = h->WB;
+  }
+  rec(h, 3);
+  launch_zfused(h->nz, false, Wz, h->Lsplit, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  rec(h, 4);
+  if (h->nranks > 1) {
+    int rc = all_to_all(h, h->WB, h->WA);
+    if (rc) return rc;
+  }
+  rec(h, 5);
+  launch_ypass(h->ny, true, h->WA, h->WB, h->Lsplit, h->Lplain, h->nzl, h->twy, h->st);
+  rec(h, 6);
+  launch_xinv(h->nx, h->WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, nrows, h->Lplain, h->twx, h->st);
+  rec(h, 7);
+  return EVP_OK;
+}
+
+// rows a4+a5+a6+a7
+int enqueue_constitutive(evp_handle h) {
+  launch_constitutive(h->f, h->nsmax, h->d_partials, &h->nblocks, h->st);
+  launch_reduce(h->d_partials, h->nblocks, h->d_totals, h->st);
+  if (h->nranks > 1) {
+    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, h->comm, h->st);
+    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, h->comm, h->st);
+    if (rc) return nccl_check(h, rc, "nccl allreduce");
+  }
+  launch_macro(h->d_totals, h->d_macro, h->Ntot, h->st);
+  rec(h, 8);
+  return EVP_OK;
+}
+
+int fetch_report(evp_handle h, evp_iter_report *rep) {
+  CUDA_OK(h, cudaMemcpyAsync(h->h_macro, h->d_macro, sizeof(MacroDev), cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  const MacroDev &m = *h->h_macro;
+  if (rep) {
+    rep->iter = m.iter;
+    rep->newton_max = m.newton_max;
+    rep->newton_mean = m.newton_mean;
+    rep->err_stress = m.err_s;
+    rep->err_strain = m.err_e;
+    for (int c = 0; c < 6; ++c) { rep->savg[c] = m.savg[c]; rep->emacro[c] = m.E[c]; }
+    rep->converged = (m.iter >= h->ctrl.itmin && m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
+    rep->nonfinite = m.nonfinite;
+  }
+  if ((h->flags & 1) && h->ev_made) {
+    for (int i = 0; i < 8; ++i) h->last_ms[i] = 0;
+    float ms;
+    auto dtm = [&](int a, int b) { return cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) == cudaSuccess ? (double)ms : 0.0; };
+    h->last_ms[0] = dtm(0, 1); h->last_ms[1] = dtm(1, 2); h->last_ms[6] = dtm(2, 3) + dtm(4, 5);
+    h->last_ms[2] = dtm(3, 4); h->last_ms[3] = dtm(5, 6); h->last_ms[4] = dtm(6, 7); h->last_ms[5] = dtm(7, 8);
+    h->last_ms[7] = dtm(0, 8);
+  }
+  return m.nonfinite ? fail(h, EVP_ERR_NUMERIC, "Newton produced a non-finite value / bad pivot") : EVP_OK;
+}
+
+evp_handle g_active = nullptr;  // handle whose tables currently sit in __constant__ memory
+
+int upload_const(evp_handle h) {
+  h->cp.dt = h->dt;
+  h->cp.tol_newton = h->ctrl.tol_newton;
+  h->cp.newton_itmax = h->ctrl.newton_itmax;
+  upload_const_params(h->cp);
+  return EVP_OK;
+}
+
+// __constant__ tables are per process: re-upload when another handle ran last
+void activate(evp_handle h) {
+  cudaSetDevice(h->device);
+  if (g_active == h) return;
+  upload_phase_tables(h->phd.data(), h->nphases);
+  if (h->have_c0) upload_green(h->green);
+  upload_const(h);
+  g_active = h;
+}
+
+}  // namespace
+
+extern "C" {
+
+int evp_abi_version(void) { return EVP_ABI_VERSION; }
+const char *evp_backend(void) { return "cuda-sm100a"; }
+const char *evp_last_error(evp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int evp_nccl_unique_id(uint8_t id[128]) {
+  std::string e;
+  if (!load_nccl(&e)) return fail(nullptr, EVP_ERR_DEVICE, e);
+  return g_nccl.GetUniqueId(id) == 0 ? EVP_OK : EVP_ERR_DEVICE;
+}
+
+int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, const evp_dist *dist, evp_handle *out) {
+  if (!grid || !phases || !out || nphases < 1 || nphases > EVP_MAX_PHASES) return fail(nullptr, EVP_ERR_ARG, "evp_create: bad argument");
+  const int nranks = dist ? dist->nranks : 1, rank = dist ? dist->rank : 0, device = dist ? dist->device : 0;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, EVP_ERR_ARG, "evp_create: bad rank/nranks");
+  if (!fft_size_supported(grid->nx) || !fft_size_supported(grid->ny) || !fft_size_supported(grid->nz))
+    return fail(nullptr, EVP_ERR_UNSUPPORTED, "grid sizes must be powers of two in [8, 1024]");
+  if (grid->nz % nranks || grid->ny % nranks) return fail(nullptr, EVP_ERR_UNSUPPORTED, "ny and nz must be divisible by nranks");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+    return fail(nullptr, EVP_ERR_DEVICE, "no CUDA device: this library has no CPU fallback");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, EVP_ERR_DEVICE, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, EVP_ERR_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", library is built for sm_100a only");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EVP_ERR_DEVICE, "cudaSetDevice failed");
+
+  evp_solver *S = new evp_solver();
+  evp_handle h = S;
+  S->g = *grid;
+  if (!(S->g.dx > 0)) S->g.dx = 1.0;
+  if (!(S->g.dy > 0)) S->g.dy = 1.0;
+  if (!(S->g.dz > 0)) S->g.dz = 1.0;
+  S->nx = grid->nx; S->ny = grid->ny; S->nz = grid->nz;
+  S->nxh = S->nx / 2 + 1;
+  S->nxp = (S->nxh + 7) / 8 * 8;
+  S->nranks = nranks; S->rank = rank; S->device = device;
+  S->nzl = S->nz / nranks; S->z0 = rank * S->nzl;
+  S->nyl = S->ny / nranks; S->ky0 = rank * S->nyl;
+  S->N = (long long)S->nx * S->ny * S->nzl;
+  S->Ntot = (double)S->nx * S->ny * S->nz;
+  S->nphases = nphases;
+  S->ph.assign(phases, phases + nphases);
+  S->phd.resize(nphases);
+  bool any_twin = false;
+  for (int p = 0; p < nphases; ++p) {
+    if (phases[p].nsys < 0 || phases[p].nsys > EVP_MAX_SYS || phases[p].nmodes < 0 || phases[p].nmodes > EVP_MAX_MODES) {
+      delete S;
+      return fail(nullptr, EVP_ERR_ARG, "phase: nsys/nmodes out of range");
+    }
+    build_phase_dev(phases[p], S->phd[p]);
+    S->nsmax = std::max(S->nsmax, (int)phases[p].nsys);
+    for (int m = 0; m < phases[p].nmodes; ++m) any_twin |= phases[p].twin[m] != 0;
+  }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+      evp_destroy(S);                                                                              \
+      return fail(nullptr, EVP_ERR_DEVICE, m_);                                                    \
+    }                                                                                              \
+  } while (0)
+  CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+  const long long N = S->N;
+  const int ns = std::max(S->nsmax, 1);
+  S->f.N = N;
+  CK(cudaMalloc(&S->f.sig, sizeof(double) * 6 * N));
+  CK(cudaMalloc(&S->f.e, sizeof(double) * 6 * N));
+  CK(cudaMalloc(&S->f.epsp, sizeof(double) * 6 * N));
+  CK(cudaMalloc(&S->f.edotp, sizeof(double) * 6 * N));
+  CK(cudaMalloc(&S->f.crss, sizeof(double) * ns * N));
+  CK(cudaMalloc(&S->f.rot, sizeof(double) * 9 * N));
+  CK(cudaMalloc(&S->f.gacc, sizeof(double) * N));
+  if (any_twin) CK(cudaMalloc(&S->f.twinf, sizeof(double) * ns * N));
+  CK(cudaMalloc(&S->f.grain, sizeof(int32_t) * N));
+  CK(cudaMalloc(&S->f.phase, sizeof(int32_t) * N));
+  // spectral work buffers (half spectrum, 6 components)
+  const size_t wbytes = sizeof(double2) * 6 * (size_t)S->nzl * S->ny * S->nxp;
+  CK(cudaMalloc(&S->WA, wbytes));
+  CK(cudaMemsetAsync(S->WA, 0, wbytes, S->st));
+  if (nranks > 1) {
+    CK(cudaMalloc(&S->WB, wbytes));
+    CK(cudaMemsetAsync(S->WB, 0, wbytes, S->st));
+  } else {
+    S->WB = S->WA;
+  }
+  S->Lplain.nyl = S->ny; S->Lplain.nzl = S->nzl; S->Lplain.nxp = S->nxp; S->Lplain.nxh = S->nxh;
+  S->Lplain.zstride = (long long)S->ny * S->nxp;
+  S->Lplain.cstride = (long long)S->nzl * S->Lplain.zstride;
+  S->Lplain.dstride = 6 * S->Lplain.cstride;
+  S->Lsplit.nyl = S->nyl; S->Lsplit.nzl = S->nzl; S->Lsplit.nxp = S->nxp; S->Lsplit.nxh = S->nxh;
+  S->Lsplit.zstride = (long long)S->nyl * S->nxp;
+  S->Lsplit.cstride = (long long)S->nzl * S->Lsplit.zstride;
+  S->Lsplit.dstride = 6 * S->Lsplit.cstride;
+  S->twx = make_twiddles(S->nx); S->twy = make_twiddles(S->ny); S->twz = make_twiddles(S->nz);
+  if (!S->twx || !S->twy || !S->twz) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "twiddle allocation failed"); }
+  CK(cudaMalloc(&S->d_macro, sizeof(MacroDev)));
+  CK(cudaMemset(S->d_macro, 0, sizeof(MacroDev)));
+  CK(cudaMallocHost(&S->h_macro, sizeof(MacroDev)));
+  std::memset(S->h_macro, 0, sizeof(MacroDev));
+  const int nb = (int)((N + constitutive_block() - 1) / constitutive_block());
+  CK(cudaMalloc(&S->d_partials, sizeof(double) * kPartial * (size_t)nb));
+  CK(cudaMalloc(&S->d_totals, sizeof(double) * 64));
+  if (nranks > 1) {
+    std::string e;
+    if (!load_nccl(&e)) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, e); }
+    Id128 id;
+    std::memcpy(id.b, dist->nccl_id, 128);
+    const int rc = g_nccl.CommInitRank(&S->comm, nranks, id, rank);
+    if (rc) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "ncclCommInitRank failed"); }
+  }
+  CK(cudaStreamSynchronize(S->st));
+#undef CK
+  (void)h;
+  *out = S;
+  return EVP_OK;
+}
+
+int evp_destroy(evp_handle h) {
+  if (!h) return EVP_OK;
+  if (g_active == h) g_active = nullptr;
+  cudaSetDevice(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
+  cudaFree(h->f.rot); cudaFree(h->f.gacc); cudaFree(h->f.twinf); cudaFree(h->f.de); cudaFree(h->f.grain); cudaFree(h->f.phase);
+  if (h->WB && h->WB != h->WA) cudaFree(h->WB);
+  cudaFree(h->WA);
+  cudaFree(h->twx); cudaFree(h->twy); cudaFree(h->twz);
+  cudaFree(h->d_macro); cudaFree(h->d_partials); cudaFree(h->d_totals);
+  if (h->h_macro) cudaFreeHost(h->h_macro);
+  if (h->ev_made) for (auto &e : h->ev) cudaEventDestroy(e);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return EVP_OK;
+}
+
+int evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl) {
+  if (!h) return EVP_ERR_ARG;
+  if (z0) *z0 = h->z0;
+  if (nzl) *nzl = h->nzl;
+  return EVP_OK;
+}
+int evp_nsys_max(evp_handle h) { return h ? h->nsmax : EVP_ERR_ARG; }
+void *evp_stream(evp_handle h) { return h ? (void *)h->st : nullptr; }
+
+int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *phase, const double *rot9) {
+  if (!h || !grain || !rot9) return fail(h, EVP_ERR_ARG, "set_microstructure: null pointer");
+  cudaSetDevice(h->device);
+  const long long N = h->N;
+  if (phase)
+    for (long long v = 0; v < N; ++v)
+      if (phase[v] < 0 || phase[v] >= h->nphases) return fail(h, EVP_ERR_ARG, "set_microstructure: phase id out of range");
+  CUDA_OK(h, cudaMemcpyAsync(h->f.grain, grain, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
+  if (phase) CUDA_OK(h, cudaMemcpyAsync(h->f.phase, phase, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
+  else CUDA_OK(h, cudaMemsetAsync(h->f.phase, 0, sizeof(int32_t) * N, h->st));
+  CUDA_OK(h, cudaMemcpyAsync(h->f.rot, rot9, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.sig, 0, sizeof(double) * 6 * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.e, 0, sizeof(double) * 6 * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.epsp, 0, sizeof(double) * 6 * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.edotp, 0, sizeof(double) * 6 * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.gacc, 0, sizeof(double) * N, h->st));
+  if (h->f.twinf) CUDA_OK(h, cudaMemsetAsync(h->f.twinf, 0, sizeof(double) * std::max(h->nsmax, 1) * N, h->st));
+  if (h->f.de) CUDA_OK(h, cudaMemsetAsync(h->f.de, 0, sizeof(double) * 6 * N, h->st));
+  activate(h);
+  launch_init_crss(h->f, h->nsmax, h->st);
+  {
+    MacroDev &m = *h->h_macro;
+    for (int c = 0; c < 6; ++c) { m.E[c] = m.Et[c] = m.dEpend[c] = m.savg[c] = m.epavg[c] = 0.0; h->Et[c] = 0; h->Edot_prev[c] = 0; }
+    m.err_s = m.err_e = m.newton_mean = 0.0;
+    m.newton_max = m.nonfinite = m.iter = 0;
+    CUDA_OK(h, cudaMemcpyAsync(h->d_macro, &m, sizeof(MacroDev), cudaMemcpyHostToDevice, h->st));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  CUDA_OK(h, cudaGetLastError());
+  h->have_micro = true; h->in_incr = false;
+  return EVP_OK;
+}
+
+int evp_set_reference_medium(evp_handle h, const double *c0) {
+  if (!h) return EVP_ERR_ARG;
+  if (c0) {
+    voigt_to_mandel(c0, h->C0m);
+  } else {
+    if (!h->have_micro) return fail(h, EVP_ERR_STATE, "reference medium average needs the microstructure");
+    // Voigt average of the rotated crystal stiffnesses: one-off set-up reduction, done on the host
+    // from the device-resident orientation field (not on the hot path)
+    const long long N = h->N;
+    std::vector<double> rot((size_t)9 * N);
+    std::vector<int32_t> phs((size_t)N);
+    CUDA_OK(h, cudaMemcpy(rot.data(), h->f.rot, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost));
+    CUDA_OK(h, cudaMemcpy(phs.data(), h->f.phase, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    std::vector<double> Cm((size_t)36 * h->nphases);
+    for (int p = 0; p < h->nphases; ++p) voigt_to_mandel(h->ph[p].c_voigt, &Cm[36 * p]);
+    double acc[36] = {0};
+#pragma omp parallel for schedule(static) reduction(+ : acc[:36])
+    for (long long v = 0; v < N; ++v) {
+      double R[9], Q[36], T[36];
+      for (int k = 0; k < 9; ++k) R[k] = rot[(size_t)k * N + v];
+      mandel_rotation(R, Q);
+      const double *C = &Cm[36 * phs[v]];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+          double s = 0;
+          for (int k = 0; k < 6; ++k) s += Q[6 * i + k] * C[6 * k + j];
+          T[6 * i + j] = s;
+        }
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+          double s = 0;
+          for (int k = 0; k < 6; ++k) s += T[6 * i + k] * Q[6 * j + k];
+          acc[6 * i + j] += s;
+        }
+    }
+    if (h->nranks > 1) {
+      CUDA_OK(h, cudaMemcpyAsync(h->d_totals + 16, acc, sizeof(acc), cudaMemcpyHostToDevice, h->st));
+      int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 36, kNcclDouble, kNcclSum, h->comm, h->st);
+      if (rc) return nccl_check(h, rc, "nccl allreduce (C0)");
+      CUDA_OK(h, cudaMemcpyAsync(acc, h->d_totals + 16, sizeof(acc), cudaMemcpyDeviceToHost, h->st));
+      CUDA_OK(h, cudaStreamSynchronize(h->st));
+    }
+    for (int k = 0; k < 36; ++k) h->C0m[k] = acc[k] / h->Ntot;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i + 1; j < 6; ++j) h->C0m[6 * i + j] = h->C0m[6 * j + i] = 0.5 * (h->C0m[6 * i + j] + h->C0m[6 * j + i]);
+  }
+  if (!inv6(h->C0m, h->S0m)) return fail(h, EVP_ERR_NUMERIC, "reference medium is singular");
+  build_s0b(h->S0m, h->cp.S0b, &h->cp.iso_c0);
+  GreenConst G;
+  build_green_const(h->C0m, h->S0m, G);
+  h->green = G;
+  h->have_c0 = true;
+  g_active = nullptr;
+  activate(h);
+  if (h->have_loading) {  // Mmac depends on C0
+    int32_t iu[9], is[6];
+    double u[9], s[6];
+    std::memcpy(iu, h->iudot, sizeof(iu)); std::memcpy(is, h->iscau, sizeof(is));
+    std::memcpy(u, h->udot, sizeof(u)); std::memcpy(s, h->scau, sizeof(s));
+    return evp_set_loading(h, iu, u, is, s);
+  }
+  return EVP_OK;
+}
+
+int evp_get_reference_medium(evp_handle h, double *c0) {
+  if (!h || !c0 || !h->have_c0) return EVP_ERR_STATE;
+  for (int a = 0; a < 6; ++a)
+    for (int b = 0; b < 6; ++b) c0[6 * a + b] = h->C0m[6 * a + b] / (kW[a] * kW[b]);
+  return EVP_OK;
+}
+
+int evp_set_control(evp_handle h, const evp_ctrl *c) {
+  if (!h || !c) return EVP_ERR_ARG;
+  h->ctrl = *c;
+  g_active = nullptr;
+  activate(h);
+  return EVP_OK;
+}
+
+int evp_set_loading(evp_handle h, const int32_t iudot[9], const double udot[9], const int32_t iscau[6], const double scau[6]) {
+  if (!h || !iudot || !udot || !iscau || !scau) return fail(h, EVP_ERR_ARG, "set_loading: null pointer");
+  bool sc[6];
+  for (int c = 0; c < 6; ++c) {
+    const int i = kI[c], j = kJ[c];
+    sc[c] = iudot[3 * i + j] && iudot[3 * j + i];
+    if (sc[c] == (iscau[c] != 0)) return fail(h, EVP_ERR_ARG, "set_loading: each symmetric component needs exactly one of strain-rate / stress imposed");
+  }
+  for (int c = 0; c < 6; ++c) h->strain_ctl[c] = sc[c];
+  for (int k = 0; k < 9; ++k) { h->iudot[k] = iudot[k]; h->udot[k] = udot[k]; }
+  for (int k = 0; k < 6; ++k) { h->iscau[k] = iscau[k]; h->scau[k] = scau[k]; }
+  h->have_loading = true;
+  if (h->have_c0) {
+    // dE_T = (C0_TT)^-1 W (scau - savg)_T / W, embedded into a 6x6 acting on Cartesian components
+    MacroDev &m = *h->h_macro;
+    std::memset(m.Mmac, 0, sizeof(m.Mmac));
+    int idx[6], nt = 0;
+    for (int c = 0; c < 6; ++c)
+      if (!sc[c]) idx[nt++] = c;
+    if (nt) {
+      for (int col = 0; col < nt; ++col) {
+        double A[36], r[6] = {0, 0, 0, 0, 0, 0};
+        for (int a = 0; a < nt; ++a)
+          for (int b = 0; b < nt; ++b) A[nt * a + b] = h->C0m[6 * idx[a] + idx[b]];
+        r[col] = 1.0;
+        solve_n(nt, A, r);
+        for (int a = 0; a < nt; ++a) m.Mmac[6 * idx[a] + idx[col]] = r[a] * kW[idx[col]] / kW[idx[a]];
+      }
+    }
+    for (int c = 0; c < 6; ++c) m.scau[c] = scau[c];
+    CUDA_OK(h, cudaMemcpyAsync(h->d_macro->Mmac, m.Mmac, sizeof(m.Mmac), cudaMemcpyHostToDevice, h->st));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_macro->scau, m.scau, sizeof(m.scau), cudaMemcpyHostToDevice, h->st));
+    CUDA_OK(h, cudaStreamSynchronize(h->st));
+  }
+  return EVP_OK;
+}
+
+int evp_begin_increment(evp_handle h, double dt) {
+  if (!h) return EVP_ERR_ARG;
+  if (!h->have_micro || !h->have_c0 || !h->have_loading) return fail(h, EVP_ERR_STATE, "begin_increment: microstructure, reference medium and loading must be set");
+  if (!(dt > 0)) return fail(h, EVP_ERR_ARG, "dt must be positive");
+  h->dt = dt;
+  g_active = nullptr;
+  activate(h);
+  MacroDev &m = *h->h_macro;
+  for (int c = 0; c < 6; ++c) {
+    const int i = kI[c], j = kJ[c];
+    const double rate = h->strain_ctl[c] ? 0.5 * (h->udot[3 * i + j] + h->udot[3 * j + i]) : h->Edot_prev[c];
+    m.dEpend[c] = dt * rate;
+    m.Et[c] = h->Et[c];
+    m.E[c] = h->Et[c] + m.dEpend[c];
+  }
+  m.iter = 0;
+  CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));  // E, Et, dEpend
+  CUDA_OK(h, cudaMemcpyAsync(&h->d_macro->iter, &m.iter, sizeof(int), cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  h->in_incr = true;
+  return EVP_OK;
+}
+
+int evp_op_green(evp_handle h) {
+  if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_green outside an increment");
+  activate(h);
+  int rc = enqueue_green(h);
+  if (rc) return rc;
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  CUDA_OK(h, cudaGetLastError());
+  return EVP_OK;
+}
+
+int evp_op_constitutive(evp_handle h, evp_iter_report *rep) {
+  if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_constitutive outside an increment");
+  activate(h);
+  int rc = enqueue_constitutive(h);
+  if (rc) return rc;
+  rc = fetch_report(h, rep);
+  CUDA_OK(h, cudaGetLastError());
+  return rc;
+}
+
+int evp_equilibrium_iter(evp_handle h, evp_iter_report *rep) {
+  if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iter outside an increment");
+  activate(h);
+  int rc = enqueue_green(h);
+  if (rc == 0) rc = enqueue_constitutive(h);
+  if (rc) return rc;
+  rc = fetch_report(h, rep);
+  CUDA_OK(h, cudaGetLastError());
+  return rc;
+}
+
+int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
+  if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iters outside an increment");
+  activate(h);
+  for (int i = 0; i < n; ++i) {
+    int rc = enqueue_green(h);
+    if (rc == 0) rc = enqueue_constitutive(h);
+    if (rc) return rc;
+  }
+  int rc = fetch_report(h, last);
+  CUDA_OK(h, cudaGetLastError());
+  return rc;
+}
+
+int evp_end_increment(evp_handle h, evp_step_report *rep) {
+  if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "end_increment outside an increment");
+  activate(h);
+  int nb = 0;
+  launch_commit(h->f, h->nsmax, h->dt, h->d_partials, &nb, h->st);
+  launch_reduce(h->d_partials, nb, h->d_totals + 16, h->st);
+  if (h->nranks > 1) {
+    int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 10, kNcclDouble, kNcclSum, h->comm, h->st);
+    if (rc) return nccl_check(h, rc, "nccl allreduce (commit)");
+  }
+  double tot[11];
+  CUDA_OK(h, cudaMemcpyAsync(tot, h->d_totals + 16, sizeof(tot), cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaMemcpyAsync(h->h_macro, h->d_macro, sizeof(MacroDev), cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  CUDA_OK(h, cudaGetLastError());
+  MacroDev &m = *h->h_macro;
+  // the pending macro correction belongs to an iteration that will not run
+  for (int c = 0; c < 6; ++c) {
+    m.E[c] -= m.dEpend[c];
+    m.dEpend[c] = 0.0;
+    h->Edot_prev[c] = (m.E[c] - h->Et[c]) / h->dt;
+    h->Et[c] = m.E[c];
+    m.Et[c] = m.E[c];
+  }
+  CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  h->in_incr = false;
+  if (rep) {
+    rep->iters = m.iter;
+    rep->err_stress = m.err_s; rep->err_strain = m.err_e;
+    rep->converged = (m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
+    for (int c = 0; c < 6; ++c) { rep->savg[c] = m.savg[c]; rep->emacro[c] = m.E[c]; rep->epavg[c] = tot[2 + c] / h->Ntot; }
+  }
+  return EVP_OK;
+}
+
+int evp_step(evp_handle h, double dt, evp_step_report *rep) {
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = evp_begin_increment(h, dt);
+  if (rc) return rc;
+  evp_iter_report ir{};
+  for (int it = 0; it < h->ctrl.itmax; ++it) {
+    rc = evp_equilibrium_iter(h, &ir);
+    if (rc) return rc;
+    if (ir.converged) break;
+  }
+  rc = evp_end_increment(h, rep);
+  if (rep) rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+int evp_field_components(evp_handle h, evp_field f) { return h ? (int)field_comps(h, f) : EVP_ERR_ARG; }
+
+int evp_get_field(evp_handle h, evp_field f, void *host, size_t bytes) {
+  if (!h || !host) return EVP_ERR_ARG;
+  cudaSetDevice(h->device);
+  size_t el;
+  void *p = field_ptr(h, f, &el);
+  const size_t need = field_comps(h, f) * (size_t)h->N * el;
+  if (field_comps(h, f) == 0) return fail(h, EVP_ERR_ARG, "unknown field");
+  if (bytes != need) return fail(h, EVP_ERR_ARG, "get_field: size mismatch");
+  if (!p) {  // optional field that was never allocated (twin fractions without twins, strain increment)
+    std::memset(host, 0, need);
+    return EVP_OK;
+  }
+  CUDA_OK(h, cudaMemcpyAsync(host, p, need, cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  return EVP_OK;
+}
+
+int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
+  if (!h || !host) return EVP_ERR_ARG;
+  cudaSetDevice(h->device);
+  size_t el;
+  void *p = field_ptr(h, f, &el);
+  const size_t need = field_comps(h, f) * (size_t)h->N * el;
+  if (field_comps(h, f) == 0) return fail(h, EVP_ERR_ARG, "unknown field");
+  if (bytes != need) return fail(h, EVP_ERR_ARG, "set_field: size mismatch");
+  if (!p) return fail(h, EVP_ERR_STATE, "field is not allocated in this configuration");
+  CUDA_OK(h, cudaMemcpyAsync(p, host, need, cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  return EVP_OK;
+}
+
+int evp_get_macro(evp_handle h, double emacro[6], double savg[6]) {
+  if (!h) return EVP_ERR_ARG;
+  cudaSetDevice(h->device);
+  CUDA_OK(h, cudaMemcpyAsync(h->h_macro, h->d_macro, sizeof(MacroDev), cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  for (int c = 0; c < 6; ++c) {
+    if (emacro) emacro[c] = h->h_macro->E[c];
+    if (savg) savg[c] = h->h_macro->savg[c];
+  }
+  return EVP_OK;
+}
+
+int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
+  if (!h || !out || comp < 0 || comp > 5) return EVP_ERR_ARG;
+  if (h->nranks != 1) return fail(h, EVP_ERR_UNSUPPORTED, "debug_spectrum: single-rank handles only");
+  activate(h);
+  launch_xfwd(h->nx, h->f.sig, h->WA, h->N, h->ny * h->nzl, h->Lplain, h->twx, h->st);
+  launch_ypass(h->ny, false, h->WA, h->WA, h->Lplain, h->Lplain, h->nzl, h->twy, h->st);
+  launch_zfused(h->nz, true, h->WA, h->Lplain, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
+                               sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  CUDA_OK(h, cudaGetLastError());
+  return EVP_OK;
+}
+
+int evp_set_profiling(evp_handle h, int32_t on) {
+  if (!h) return EVP_ERR_ARG;
+  cudaSetDevice(h->device);
+  h->flags = on;
+  if ((on & 1) && !h->ev_made) {
+    for (auto &e : h->ev) CUDA_OK(h, cudaEventCreate(&e));
+    h->ev_made = true;
+  }
+  if ((on & 2) && !h->f.de) {
+    CUDA_OK(h, cudaMalloc(&h->f.de, sizeof(double) * 6 * h->N));
+    CUDA_OK(h, cudaMemset(h->f.de, 0, sizeof(double) * 6 * h->N));
+  }
+  return EVP_OK;
+}
+
+int evp_last_kernel_ms(evp_handle h, double ms[8]) {
+  if (!h || !ms) return EVP_ERR_ARG;
+  for (int i = 0; i < 8; ++i) ms[i] = h->last_ms[i];
+  return EVP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// tests/emu/emu.cpp — TEST INFRASTRUCTURE ONLY.  Runs the thread-level math of the CUDA kernels
+// (lapx_b200/csrc/evp_core.h, the very same inline functions the __global__ kernels call) on the
+// CPU, so that the arithmetic can be checked in the GPU-less build container.  It is not part of
+// the product library and is not reachable from the product API.
+#include <cstring>
+#include <vector>
+
+#include "../../lapx_b200/csrc/host_math.h"
+
+using namespace evp;
+using namespace evp::host;
+
+namespace {
+
+struct OffLin { int base; int operator()(int i) const { return base + i; } };
+struct TwTab { const double2 *t; double2 operator()(int k) const { return t[k]; } };
+
+template <int N, int R, int NS, bool INV>
+void emu_pass(double2 *s, int nlines, const double2 *tw) {
+  std::vector<double2> regs((size_t)nlines * (N / 8) * 8);
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 8; ++q) pass_load<N, R>(s, q, &regs[((size_t)l * (N / 8) + q) * 8], OffLin{l * N});
+  // (the kernel has __syncthreads() here)
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 8; ++q) pass_store<N, R, NS, INV>(s, q, &regs[((size_t)l * (N / 8) + q) * 8], OffLin{l * N}, TwTab{tw});
+}
+template <int N, int NS, bool INV>
+void emu_rest(double2 *s, int nlines, const double2 *tw) {
+  if constexpr (NS < N) {
+    emu_pass<N, 8, NS, INV>(s, nlines, tw);
+    emu_rest<N, NS * 8, INV>(s, nlines, tw);
+  }
+}
+template <int N, bool INV>
+void emu_fft_n(double2 *s, int nlines, const double2 *tw) {
+  constexpr int R0 = first_radix(N);
+  emu_pass<N, R0, 1, INV>(s, nlines, tw);
+  emu_rest<N, R0, INV>(s, nlines, tw);
+}
+
+struct ItcArr { const double *p; double operator()(int s) const { return p[s]; } };
+
+}  // namespace
+
+extern "C" {
+
+// in-place FFT of nlines contiguous lines of length n (interleaved re,im); same pass sequence as block_fft
+int emu_fft(int n, int inv, int nlines, double *data) {
+  std::vector<double2> tw(n);
+  for (int k = 0; k < n; ++k) {
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+    tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  double2 *s = reinterpret_cast<double2 *>(data);
+#define E_(N) case N: if (inv) emu_fft_n<N, true>(s, nlines, tw.data()); else emu_fft_n<N, false>(s, nlines, tw.data()); return 0;
+  switch (n) { E_(8) E_(16) E_(32) E_(64) E_(128) E_(256) E_(512) E_(1024) default: return -1; }
+#undef E_
+}
+
+// one voxel of k_constitutive.  c0_voigt: reference medium.  Returns Newton iterations.
+int emu_constitutive(const evp_phase *ph, const double *c0_voigt, const double *R, double *sig, const double *e, const double *epsp,
+                     const double *crss, double dt, double tol, int itmax, double *ds, double *de, int *bad, int force_aniso) {
+  PhaseDev P;
+  build_phase_dev(*ph, P);
+  double C0m[36], S0m[36];
+  voigt_to_mandel(c0_voigt, C0m);
+  inv6(C0m, S0m);
+  ConstParams cp;
+  build_s0b(S0m, cp.S0b, &cp.iso_c0);
+  if (force_aniso) cp.iso_c0 = 0;
+  cp.dt = dt; cp.tol_newton = tol; cp.newton_itmax = itmax;
+  double itc[EVP_MAX_SYS], em[6];
+  for (int s = 0; s < ph->nsys; ++s) itc[s] = 1.0 / crss[s];
+  for (int c = 0; c < 6; ++c) em[c] = e[c] - epsp[c];
+  *bad = 0;
+  return constitutive_voxel(P, cp, R, sig, em, ItcArr{itc}, ds, de, bad);
+}
+
+// Green operator at one frequency (k_zfused inner stage).  lam/out: 6 complex (re,im interleaved)
+int emu_green_point(const double *c0_voigt, double x, double y, double z, int zero, int nyq, double scale, const double *lam, double *out) {
+  double C0m[36], S0m[36];
+  voigt_to_mandel(c0_voigt, C0m);
+  inv6(C0m, S0m);
+  GreenConst G;
+  build_green_const(C0m, S0m, G);
+  double2 l[6], o[6];
+  for (int c = 0; c < 6; ++c) l[c] = make_double2(lam[2 * c], lam[2 * c + 1]);
+  green_point(G, x, y, z, zero != 0, nyq != 0, scale, l, o);
+  for (int c = 0; c < 6; ++c) { out[2 * c] = o[c].x; out[2 * c + 1] = o[c].y; }
+  return 0;
+}
+
+int emu_rot_b5(const double *R, double *M) { rot_b5(R, M); return 0; }
+
+}  // extern "C"

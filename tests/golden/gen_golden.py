@@ -278,7 +278,7 @@ class NumpyEVP:
         return np.ascontiguousarray((v6 / self.W).T).reshape((6,) + self.shape)
 
 
-def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs, phase=None, hcp=False):
+def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs, phase=None, hcp=False, slim=False):
     nx, ny, nz = grid
     ids, grot = ms.voronoi(lib, grid, ngrains, seed)
     if phase is None:
@@ -304,6 +304,9 @@ def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs,
         fields[f"e_end_inc{inc}"] = S.field(S.e)
         fields[f"epsp_end_inc{inc}"] = S.field(S.epsp)
         fields[f"crss_end_inc{inc}"] = np.ascontiguousarray(S.crss.T).reshape((S.ns, nz, ny, nx))
+    if slim:  # keep the fixture small: final stress and strain only
+        last = nincs - 1
+        fields = {k: v for k, v in fields.items() if k in (f"sig_end_inc{last}", f"e_end_inc{last}")}
     c0v = S.C0m / np.outer(S.W, S.W)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
     np.savez_compressed(
@@ -319,6 +322,7 @@ def main():
     D = np.diag([-0.5, -0.5, 1.0])
     make_case(lib, "fcc8_strain", (8, 8, 8), 6, 0, api.Loading.strain_rate(D), 2e-4, 12, 2)
     make_case(lib, "fcc_12x10x8_tension", (12, 10, 8), 9, 3, api.Loading.uniaxial_tension(1.0), 2e-4, 10, 2)
+    make_case(lib, "fcc_16x8x32_tension", (16, 8, 32), 12, 5, api.Loading.uniaxial_tension(1.0), 2e-4, 8, 2, slim=True)
     hcp = ms.hcp_phase(lib, with_twin=1, nrate=10.0,
                        voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
     make_case(lib, "hcp8_compression", (8, 8, 8), 5, 7, api.Loading.strain_rate(-D), 2e-4, 10, 2, phase=hcp, hcp=True)

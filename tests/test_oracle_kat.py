@@ -1,0 +1,119 @@
+"""CPU: known-answer tests that anchor the oracle to physics, since no reference
+implementation is available to pin it (PARITY UNPINNED)."""
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+from common import make_polycrystal, rel_err
+from lapx_b200 import api, microstructure as ms
+
+
+def test_fft_matches_scipy(oracle_lib, product_lib):
+    rng = np.random.default_rng(0)
+    for grid in [(8, 8, 8), (12, 10, 6), (16, 8, 32), (9, 15, 5)]:
+        s, ids, grot = make_polycrystal(oracle_lib, product_lib, grid, 4)
+        nx, ny, nz = grid
+        f = rng.normal(size=(6, nz, ny, nx))
+        s.set_field(api.FIELD_STRESS, f)
+        for comp in (0, 3, 5):
+            spec = s.debug_spectrum(comp)
+            ref = sfft.rfftn(f[comp], axes=(0, 1, 2))
+            assert np.abs(spec - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_single_crystal_uniform_and_analytic(oracle_lib, product_lib):
+    """One grain: fields stay uniform, the iteration converges at once, and with the tensile axis along
+    [001] of a cube-oriented FCC crystal the stress follows the scalar power law analytically."""
+    ph = ms.fcc_phase(product_lib, gamma0=1.0, nrate=10.0, tau0=16.0)
+    n = 8
+    s = api.Solver(oracle_lib, (n, n, n), [ph])
+    ids = np.zeros((n, n, n), np.int32)
+    rot9 = ms.expand_rotations(ids, np.eye(3)[None])
+    s.set_microstructure(ids, None, rot9)
+    s.set_reference_medium(None)
+    s.set_control(tol_stress=1e-10, tol_strain=1e-10, itmax=200, tol_newton=1e-12, newton_itmax=200)
+    s.set_loading(api.Loading.uniaxial_tension(1.0))
+    dt = 1e-4
+    for inc in range(12):
+        rep = s.step(dt)
+        assert rep.converged
+    sig = s.get_field(api.FIELD_STRESS)
+    assert np.abs(sig - sig.reshape(6, -1)[:, :1].reshape(6, 1, 1, 1)).max() < 1e-9 * np.abs(sig).max()
+    s33 = sig[2].mean()
+    assert np.abs(sig[[0, 1, 3, 4, 5]]).max() < 1e-8 * s33
+    # analytic: 8 active systems with Schmid factor 1/sqrt6; eps_p33_dot = 8 * m33 * g0 (m33 s/tau)^n, m33 = 1/sqrt6
+    # total strain rate 1 = s33_dot / E001 + eps_p33_dot  -> implicit Euler gives the same s33 as the solver
+    m33 = 1 / np.sqrt(6)
+    c11, c12 = ms.CU_C11, ms.CU_C12
+    E001 = (c11 - c12) * (c11 + 2 * c12) / (c11 + c12)
+    sa, epa = 0.0, 0.0
+    for inc in range(12):
+        # solve  sa_new/E001 + epa + dt*8*m33*(m33*sa_new/16)^10 = (inc+1)*dt   (Newton)
+        x = sa
+        for _ in range(100):
+            f = x / E001 + epa + dt * 8 * m33 * (m33 * x / 16.0) ** 10 - (inc + 1) * dt
+            df = 1 / E001 + dt * 8 * m33 * 10 * (m33 * x / 16.0) ** 9 * m33 / 16.0
+            x -= f / df
+        sa = x
+        epa += dt * 8 * m33 * (m33 * sa / 16.0) ** 10
+    assert abs(s33 - sa) < 1e-8 * sa
+
+
+def test_laminate_traction_and_compatibility(oracle_lib, product_lib):
+    """Two-phase laminate normal to x (elastic-dominated step): sigma_1j continuous, in-plane e uniform."""
+    ph = ms.fcc_phase(product_lib, tau0=1e6)      # effectively elastic
+    nx, ny, nz = 16, 8, 8
+    s = api.Solver(oracle_lib, (nx, ny, nz), [ph])
+    ids = np.zeros((nz, ny, nx), np.int32)
+    ids[:, :, nx // 2:] = 1
+    rng = np.random.default_rng(3)
+    grot = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(2)])
+    grot *= np.sign(np.linalg.det(grot))[:, None, None]
+    s.set_microstructure(ids, None, ms.expand_rotations(ids, grot))
+    s.set_reference_medium(None)
+    s.set_control(tol_stress=1e-11, tol_strain=1e-11, itmax=2000)
+    D = np.array([[1.0, 0.2, 0.1], [0.2, -0.3, 0.0], [0.1, 0.0, -0.4]])
+    s.set_loading(api.Loading.strain_rate(D))
+    rep = s.step(1e-4)
+    assert rep.converged
+    sig = s.get_field(api.FIELD_STRESS)
+    e = s.get_field(api.FIELD_STRAIN)
+    # the laminate solution is piecewise uniform
+    for f in (sig, e):
+        for half in (slice(0, nx // 2), slice(nx // 2, nx)):
+            blk = f[:, :, :, half]
+            assert np.abs(blk - blk.mean(axis=(1, 2, 3), keepdims=True)).max() < 2e-7 * np.abs(f).max()
+    left, right = sig[:, 0, 0, 1], sig[:, 0, 0, nx - 2]
+    for c in (0, 4, 5):        # tractions on the x-plane: s11, s13, s12
+        assert abs(left[c] - right[c]) < 1e-6 * np.abs(sig).max()
+    el, er = e[:, 0, 0, 1], e[:, 0, 0, nx - 2]
+    for c in (1, 2, 3):        # in-plane strains e22, e33, e23
+        assert abs(el[c] - er[c]) < 1e-6 * np.abs(e).max()
+    assert rel_err(e.reshape(6, -1).mean(axis=1), 1e-4 * np.array([1.0, -0.3, -0.4, 0.0, 0.1, 0.2])) < 1e-9
+
+
+def test_green_operator_projector_identities(oracle_lib, product_lib):
+    """Gamma applied to C0:grad_sym(u) of a periodic displacement returns that compatible strain, and
+    applied to a divergence-free stress returns zero (both away from the Nyquist planes)."""
+    n = 12  # not a power of two, and even -> Nyquist planes exist; use band-limited fields
+    s, ids, grot = make_polycrystal(oracle_lib, product_lib, (n, n, n), 5)
+    c0 = s.get_reference_medium()
+    s.set_loading(api.Loading.strain_rate(np.zeros((3, 3))))
+    x = np.arange(n) * 2 * np.pi / n
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    # displacement u = (sin(X+2Y), cos(2Z - X), sin(Y+Z)) -> strain (tensor components)
+    e11 = np.cos(X + 2 * Y)
+    e22 = np.zeros_like(X)
+    e33 = np.cos(Y + Z)
+    e23 = 0.5 * (-2 * np.sin(2 * Z - X) * 1.0 + np.cos(Y + Z))      # (du2/dz + du3/dy)/2
+    e13 = np.zeros_like(X)
+    e12 = 0.5 * (2 * np.cos(X + 2 * Y) + np.sin(2 * Z - X))          # (du1/dy + du2/dx)/2
+    eps = np.stack([e11, e22, e33, e23, e13, e12])
+    W = np.array([1, 1, 1, 2, 2, 2.0])
+    sig = np.einsum("ab,b...->a...", c0 * W[None, :], eps)
+    s.set_field(api.FIELD_STRESS, sig)
+    s.set_field(api.FIELD_STRAIN, np.zeros_like(eps))
+    s.begin_increment(1.0)
+    s.op_green()                    # e <- 0 - Gamma*(C0:eps) = -eps
+    got = -s.get_field(api.FIELD_STRAIN)
+    assert np.abs(got - eps).max() < 1e-12 * np.abs(eps).max()
