@@ -283,7 +283,7 @@ class Solver:
         self._check(self.lib.evp_get_reference_medium(self.h, out.ctypes.data_as(C.c_void_p)))
         return out.reshape(6, 6)
 
-    def set_control(self, tol_stress=1e-6, tol_strain=1e-6, itmax=100, itmin=1, tol_newton=1e-9,
+    def set_control(self, tol_stress=1e-6, tol_strain=1e-6, itmax=100, itmin=1, tol_newton=1e-6,
                     newton_itmax=100):
         c = Ctrl(tol_stress, tol_strain, itmax, itmin, tol_newton, newton_itmax)
         self._check(self.lib.evp_set_control(self.h, C.byref(c)))

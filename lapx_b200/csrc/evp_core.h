@@ -229,6 +229,80 @@ EVP_HD int newton_crystal(const PhaseDev &P, const double Jb[21], const double g
 }
 
 
+
+// x^K with a compile-time exponent (square-and-multiply, K = n-1 of the power law)
+template <int K>
+EVP_HD double pow_ct(double x) {
+  if constexpr (K == 0) return 1.0;
+  else if constexpr (K == 1) return x;
+  else {
+    const double h = pow_ct<K / 2>(x);
+    return (K & 1) ? h * h * x : h * h;
+  }
+}
+
+// NPOW_T >= 0: every system uses the compile-time exponent n-1 = NPOW_T;  NPOW_T < 0: per-system tables
+template <int NPOW_T>
+EVP_HD void slip_rate_t(const PhaseDev &P, int s, double tau, double itc, double &gd, double &dgd) {
+  const double x = fabs(tau) * itc;
+  const double xn1 = (NPOW_T >= 0) ? pow_ct<(NPOW_T >= 0 ? NPOW_T : 0)>(x) : pow_nm1(x, P.npow[s], P.nrate[s]);
+  const bool off = (P.twin[s] != 0) && (tau <= 0.0);
+  const double g = off ? 0.0 : P.g0[s] * xn1;
+  gd = g * x * (tau >= 0.0 ? 1.0 : -1.0);
+  dgd = g * P.nrate[s] * itc;
+}
+
+// Row a4, production form.  NS_T > 0: the loop over systems is fully unrolled (tables become
+// constant-bank operands);  NS_T == 0: runtime P.nsys.  JB(k)/GV(i): accessors of the packed
+// Jb = S0_c + S_c and of g (kept in shared memory by the kernel, in arrays by the emulation).
+template <int NS_T, int NPOW_T, class JB, class GV, class ITC>
+EVP_HD int newton_crystal_t(const PhaseDev &P, JB Jb, GV g, double s[6], double dt, double tol, int itmax, ITC itc, int *bad) {
+  int it = 0;
+  while (it < itmax) {
+    double A[15], F[6];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) A[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) F[i] = g(i);
+    const int ns = (NS_T > 0) ? NS_T : P.nsys;
+#pragma unroll
+    for (int q = 0; q < ns; ++q) {
+      double tau = 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tau += P.m[q][c] * s[c];
+      double gd, dgd;
+      slip_rate_t<NPOW_T>(P, q, tau, itc(q), gd, dgd);
+      const double a = dt * gd, bcoef = dt * dgd;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) F[c] -= a * P.m[q][c];
+#pragma unroll
+      for (int k = 0; k < 15; ++k) A[k] += bcoef * P.mm[q][k];
+    }
+    double J[21];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) {
+        const double jb = Jb(sidx(i, j));
+        J[sidx(i, j)] = (i < 5 && j < 5) ? jb + A[s5idx(i, j)] : jb;
+        F[i] -= jb * s[j];
+        if (j != i) F[j] -= jb * s[i];
+      }
+    const bool ok = ldl6_solve(J, F);
+    double dn = 0.0, sn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      s[i] += F[i];
+      dn += F[i] * F[i];
+      sn += s[i] * s[i];
+    }
+    ++it;
+    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
+    if (dn <= tol * tol * sn) break;
+  }
+  return it;
+}
+
 // kernel-constant parameters of the constitutive kernel
 struct ConstParams {
   double S0b[21];           // reference compliance, b-basis, packed (sample frame)
@@ -343,6 +417,88 @@ EVP_HD int constitutive_voxel(const PhaseDev &P, const ConstParams &cp, const do
   return nit;
 }
 
+
+// Production split of constitutive_voxel: `prep` fills Jb (21), g (6), s_old (6) through the
+// store functors (shared memory in the kernel) and returns the crystal-frame initial guess in sc;
+// `finish` turns the converged crystal-frame stress into the sample-frame Cartesian stress and the
+// two norm contributions.  The rotation M is recomputed in finish to keep registers low.
+template <class STJ, class STG, class STS>
+EVP_HD void constitutive_prep(const PhaseDev &P, const ConstParams &cp, const double R[9], const double sig[6], const double em[6],
+                              STJ stJ, STG stG, STS stS, double sc[6]) {
+  double M[25];
+  rot_b5(R, M);
+  double so[6], eb[6];
+  cart_to_b(sig, so);
+  cart_to_b(em, eb);
+  double g[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double acc = eb[i];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc += cp.S0b[sidx(i, j)] * so[j];
+    g[i] = acc;
+  }
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double x = 0.0, y = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      x += M[b * 5 + a] * g[b];
+      y += M[b * 5 + a] * so[b];
+    }
+    stG(a, x);
+    sc[a] = y;
+  }
+  stG(5, g[5]);
+  sc[5] = so[5];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) stS(a, sc[a]);
+  if (cp.iso_c0) {
+#pragma unroll
+    for (int k = 0; k < 21; ++k) stJ(k, cp.S0b[k] + P.Sc[k]);
+  } else {
+    double Jb[21];
+    rotate_s0(cp.S0b, M, Jb);
+#pragma unroll
+    for (int k = 0; k < 21; ++k) stJ(k, Jb[k] + P.Sc[k]);
+  }
+}
+
+template <class JB, class SV>
+EVP_HD void constitutive_finish(const PhaseDev &P, const double R[9], const double sc[6], JB Jb, SV sold, double sig[6], double *ds,
+                                double *de) {
+  double d[6], ds2 = 0.0, de2 = 0.0, acc[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    d[a] = sc[a] - sold(a);
+    ds2 += d[a] * d[a];
+    acc[a] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      const double w = Jb(sidx(i, j)) - P.Sc[sidx(i, j)];
+      acc[i] += w * d[j];
+      if (j != i) acc[j] += w * d[i];
+    }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) de2 += acc[a] * acc[a];
+  *ds = sqrt(ds2);
+  *de = sqrt(de2);
+  double M[25], sb[6];
+  rot_b5(R, M);
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double x = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) x += M[a * 5 + b] * sc[b];
+    sb[a] = x;
+  }
+  sb[5] = sc[5];
+  b_to_cart(sb, sig);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row a2: Green operator at one frequency (vector form):
 //   A_ik = C0_ijkl xi_j xi_l, G = A^-1, t = lam.xi, u = G t, de_ij = (u_i xi_j + u_j xi_i)/2
@@ -355,26 +511,8 @@ struct GreenConst {
   double SC[36];
 };
 
-EVP_HD void green_point(const GreenConst &G0, double x, double y, double z, bool zero, bool nyq, double scale,
-                        const double2 lam[6], double2 out[6]) {
-  if (zero) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) out[c] = make_double2(0.0, 0.0);
-    return;
-  }
-  if (nyq) {
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double re = 0.0, im = 0.0;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        re += G0.SC[6 * a + b] * lam[b].x;
-        im += G0.SC[6 * a + b] * lam[b].y;
-      }
-      out[a] = make_double2(re * scale, im * scale);
-    }
-    return;
-  }
+// scaled inverse acoustic tensor g = scale * (C0 : xi xi)^-1, symmetric, order 00,01,02,11,12,22
+EVP_HD void green_G(const GreenConst &G0, double x, double y, double z, double scale, double g[6]) {
   const double p[6] = {x * x, y * y, z * z, y * z, x * z, x * y};
   double A[6];  // 00,11,22,12,02,01
 #pragma unroll
@@ -393,20 +531,56 @@ EVP_HD void green_point(const GreenConst &G0, double x, double y, double z, bool
   const double c22 = A[0] * A[1] - A[5] * A[5];
   const double det = A[0] * c00 + A[5] * c01 + A[4] * c02;
   const double id = scale / det;
-  const double g00 = c00 * id, g01 = c01 * id, g02 = c02 * id, g11 = c11 * id, g12 = c12 * id, g22 = c22 * id;
-  // t_k = lam_kl xi_l   (lam order 11,22,33,23,13,12)
-  const double t0r = lam[0].x * x + lam[5].x * y + lam[4].x * z, t0i = lam[0].y * x + lam[5].y * y + lam[4].y * z;
-  const double t1r = lam[5].x * x + lam[1].x * y + lam[3].x * z, t1i = lam[5].y * x + lam[1].y * y + lam[3].y * z;
-  const double t2r = lam[4].x * x + lam[3].x * y + lam[2].x * z, t2i = lam[4].y * x + lam[3].y * y + lam[2].y * z;
-  const double u0r = g00 * t0r + g01 * t1r + g02 * t2r, u0i = g00 * t0i + g01 * t1i + g02 * t2i;
-  const double u1r = g01 * t0r + g11 * t1r + g12 * t2r, u1i = g01 * t0i + g11 * t1i + g12 * t2i;
-  const double u2r = g02 * t0r + g12 * t1r + g22 * t2r, u2i = g02 * t0i + g12 * t1i + g22 * t2i;
-  out[0] = make_double2(u0r * x, u0i * x);
-  out[1] = make_double2(u1r * y, u1i * y);
-  out[2] = make_double2(u2r * z, u2i * z);
-  out[3] = make_double2(0.5 * (u1r * z + u2r * y), 0.5 * (u1i * z + u2i * y));
-  out[4] = make_double2(0.5 * (u0r * z + u2r * x), 0.5 * (u0i * z + u2i * x));
-  out[5] = make_double2(0.5 * (u0r * y + u1r * x), 0.5 * (u0i * y + u1i * x));
+  g[0] = c00 * id; g[1] = c01 * id; g[2] = c02 * id; g[3] = c11 * id; g[4] = c12 * id; g[5] = c22 * id;
+}
+// de = sym(u (x) xi), u = g (lam . xi): real-linear, applied to the real and imaginary parts in turn.
+// lam / out in Cartesian order 11,22,33,23,13,12.
+EVP_HD void green_apply(const double g[6], double x, double y, double z, const double lam[6], double out[6]) {
+  const double t0 = lam[0] * x + lam[5] * y + lam[4] * z;
+  const double t1 = lam[5] * x + lam[1] * y + lam[3] * z;
+  const double t2 = lam[4] * x + lam[3] * y + lam[2] * z;
+  const double u0 = g[0] * t0 + g[1] * t1 + g[2] * t2;
+  const double u1 = g[1] * t0 + g[3] * t1 + g[4] * t2;
+  const double u2 = g[2] * t0 + g[4] * t1 + g[5] * t2;
+  out[0] = u0 * x;
+  out[1] = u1 * y;
+  out[2] = u2 * z;
+  out[3] = 0.5 * (u1 * z + u2 * y);
+  out[4] = 0.5 * (u0 * z + u2 * x);
+  out[5] = 0.5 * (u0 * y + u1 * x);
+}
+// Nyquist planes: de = scale * S0 : lam  (SC acts on Cartesian 6-vectors)
+EVP_HD void green_nyquist(const GreenConst &G0, double scale, const double lam[6], double out[6]) {
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    double acc = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) acc += G0.SC[6 * a + b] * lam[b];
+    out[a] = acc * scale;
+  }
+}
+
+EVP_HD void green_point(const GreenConst &G0, double x, double y, double z, bool zero, bool nyq, double scale,
+                        const double2 lam[6], double2 out[6]) {
+  if (zero) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[c] = make_double2(0.0, 0.0);
+    return;
+  }
+  double lr[6], li[6], orr[6], oi[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { lr[c] = lam[c].x; li[c] = lam[c].y; }
+  if (nyq) {
+    green_nyquist(G0, scale, lr, orr);
+    green_nyquist(G0, scale, li, oi);
+  } else {
+    double g[6];
+    green_G(G0, x, y, z, scale, g);
+    green_apply(g, x, y, z, lr, orr);
+    green_apply(g, x, y, z, li, oi);
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) out[c] = make_double2(orr[c], oi[c]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -2,8 +2,52 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace evp {
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) + mbarrier wrappers: spectral tiles are staged global <-> shared by
+// the tensor memory accelerator; one elected thread issues the copies, the block waits on an mbarrier.
+// ---------------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void load5(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void store5(const CUtensorMap *tm, const void *src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"((uint64_t)tm),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+}  // namespace tma
 
 __constant__ PhaseDev c_phase[EVP_MAX_PHASES];
 __constant__ GreenConst c_green;
@@ -95,7 +139,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__
     const double2 A = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
     const double2 B = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
     const int row = row0 + ll;
-    const int zl = row / ny, y = row % ny;
+    const int zl = row >> Lay.lg_nyl, y = row & (ny - 1);
     const long long o = Lay.row_ysplit(2 * pair, zl, y) + k;
     W[o] = A;
     W[o + Lay.cstride] = B;
@@ -122,7 +166,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
     double2 A = make_double2(0.0, 0.0), B = A;
     if (ll < nrl) {
       const int row = row0 + ll;
-      const int zl = row / ny, y = row % ny;
+      const int zl = row >> Lay.lg_nyl, y = row & (ny - 1);
       const long long o = Lay.row_ysplit(2 * pair, zl, y) + k;
       A = W[o];
       B = W[o + Lay.cstride];
@@ -166,28 +210,41 @@ struct YCfg {
   static constexpr size_t smem = (size_t)ZT * NY * TX * sizeof(double2);
 };
 
+// Tiles move by TMA: one op per (plane, chunk of yc rows); the split (all-to-all send) layout is the
+// 5-D tensor [kx][y % nyl][zl][c][y / nyl], the plain layout is the same with nyl = ny.
 template <int NY, bool INV>
-__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const double2 *__restrict__ in, double2 *__restrict__ out, SpecLayout Lin,
-                                                       SpecLayout Lout, int nzl, const double2 *__restrict__ twp) {
+__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out,
+                                                       const double2 *__restrict__ twp) {
   using C = YCfg<NY>;
-  extern __shared__ double2 sm[];
+  extern __shared__ __align__(128) double2 sm[];
+  __shared__ uint64_t bar;
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * C::TX;
   const int z0 = blockIdx.y * C::ZT;
   const int c = blockIdx.z;
-  const int nxh = Lin.nxh;
-  for (int idx = tid; idx < C::ZT * NY * C::TX; idx += C::T) {
-    const int col = idx % C::TX, row = (idx / C::TX) % NY, zt = idx / (C::TX * NY);
-    double2 v = make_double2(0.0, 0.0);
-    if (k0 + col < nxh && z0 + zt < nzl) v = in[Lin.row_ysplit(c, z0 + zt, row) + k0 + col];
-    sm[idx] = v;
+  if (tid == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::fence_mbar_init();
   }
   __syncthreads();
+  if (tid == 0) {
+    tma::mbar_expect_tx(&bar, (uint32_t)C::smem);
+    for (int zt = 0; zt < C::ZT; ++zt)
+      for (int y0 = 0; y0 < NY; y0 += yc_in)
+        tma::load5(sm + (zt * NY + y0) * C::TX, &tin, &bar, 2 * k0, y0 & ((1 << lg_nyl_in) - 1), z0 + zt, c, y0 >> lg_nyl_in);
+  }
+  tma::mbar_wait(&bar, 0);
   const int l = tid % C::L, q = tid / C::L;
   block_fft<NY, INV>(sm, q, OffES<C::TX>{(l / C::TX) * (NY * C::TX) + (l % C::TX)}, TwLdg{twp});
-  for (int idx = tid; idx < C::ZT * NY * C::TX; idx += C::T) {
-    const int col = idx % C::TX, row = (idx / C::TX) % NY, zt = idx / (C::TX * NY);
-    if (k0 + col < nxh && z0 + zt < nzl) out[Lout.row_ysplit(c, z0 + zt, row) + k0 + col] = sm[idx];
+  tma::fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    for (int zt = 0; zt < C::ZT; ++zt)
+      for (int y0 = 0; y0 < NY; y0 += yc_out)
+        tma::store5(&tout, sm + (zt * NY + y0) * C::TX, 2 * k0, y0 & ((1 << lg_nyl_out) - 1), z0 + zt, c, y0 >> lg_nyl_out);
+    tma::commit();
+    tma::wait_read0();
   }
 }
 
@@ -199,59 +256,93 @@ template <int NZ>
 struct ZCfg {
   static constexpr int TX = (NZ >= 1024) ? 2 : ((NZ >= 256) ? 4 : 8);
   static constexpr int TPC = TX * NZ / 8;                       // threads per component
-  static constexpr int CG = (TPC >= 384) ? 1 : (2 * TPC >= 384 ? 2 : (3 * TPC >= 384 ? 3 : 6));
-  static constexpr int T = CG * TPC;
   static constexpr int CS = NZ * TX;                            // component stride in smem (elements)
   static constexpr size_t smem = (size_t)6 * CS * sizeof(double2);
+  static constexpr int MINB = (smem <= 100 * 1024) ? 2 : 1;     // two resident blocks when shared memory allows
+  static constexpr int TT = (MINB == 2) ? 256 : 512;            // thread target: 128 registers per thread either way
+  static constexpr int CG = (TPC >= TT) ? 1 : (2 * TPC >= TT ? 2 : (3 * TPC >= TT ? 3 : 6));
+  static constexpr int T = CG * TPC;
 };
 
 template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; MODE 1: forward only (evp_debug_spectrum)
-__global__ void __launch_bounds__(ZCfg<NZ>::T) k_zfused(double2 *__restrict__ Wt, SpecLayout Lay, int ky0, int nx, int ny, double rx,
-                                                        double ry, double rz, double scale, const double2 *__restrict__ twp) {
+__global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ CUtensorMap tz, int lg_nzl, int zc,
+                                                                        int ky0, int nx, int ny, double rx, double ry, double rz,
+                                                                        double scale, const double2 *__restrict__ twp) {
   using C = ZCfg<NZ>;
-  extern __shared__ double2 sm[];
+  extern __shared__ __align__(128) double2 sm[];
+  __shared__ uint64_t bar;
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * C::TX;
   const int yl = blockIdx.y;
-  const int nxh = Lay.nxh;
-  // load [c][z][TX]
-  for (int idx = tid; idx < 6 * C::CS; idx += C::T) {
-    const int col = idx % C::TX, z = (idx / C::TX) % NZ, c = idx / C::CS;
-    double2 v = make_double2(0.0, 0.0);
-    if (k0 + col < nxh) v = Wt[Lay.row_zsplit(c, z, yl) + k0 + col];
-    sm[idx] = v;
+  const int nxh = nx / 2 + 1;
+  if (tid == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::fence_mbar_init();
   }
   __syncthreads();
+  // tile [c][z][TX] by TMA: one op per (component, chunk of zc planes); z-split (recv) layout = 5-D tensor
+  // [kx][yl][z % nzl][c][z / nzl]
+  if (tid == 0) {
+    tma::mbar_expect_tx(&bar, (uint32_t)C::smem);
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c)
+#pragma unroll 1
+      for (int z0 = 0; z0 < NZ; z0 += zc)
+        tma::load5(sm + c * C::CS + z0 * C::TX, &tz, &bar, 2 * k0, yl, z0 & ((1 << lg_nzl) - 1), c, z0 >> lg_nzl);
+  }
+  tma::mbar_wait(&bar, 0);
   const int cg = tid / C::TPC, t = tid % C::TPC;
   const int col = t % C::TX, q = t / C::TX;
 #pragma unroll 1
   for (int c = cg; c < 6; c += C::CG) block_fft<NZ, false>(sm, q, OffES<C::TX>{c * C::CS + col}, TwLdg{twp});
   if (MODE == 0) {
-  // Green operator per frequency (row a2)
-  const int ky = ky0 + yl;
-  const int fy = (ky <= ny / 2) ? ky : ky - ny;
-  for (int idx = tid; idx < C::CS; idx += C::T) {
-    const int cc = idx % C::TX, kz = idx / C::TX;
-    const int kx = k0 + cc;
-    if (kx < nxh) {
-      const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
-      double2 lam[6], o[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) lam[c] = sm[c * C::CS + idx];
-      const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
-      const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
-      green_point(c_green, kx * rx, fy * ry, fz * rz, zero, nyq, scale, lam, o);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) sm[c * C::CS + idx] = o[c];
-    }
-  }
-  __syncthreads();
+    // Green operator per frequency (row a2); real and imaginary parts are transformed one after the other
+    const int ky = ky0 + yl;
+    const int fy = (ky <= ny / 2) ? ky : ky - ny;
 #pragma unroll 1
-  for (int c = cg; c < 6; c += C::CG) block_fft<NZ, true>(sm, q, OffES<C::TX>{c * C::CS + col}, TwLdg{twp});
+    for (int idx = tid; idx < C::CS; idx += C::T) {
+      const int cc = idx % C::TX, kz = idx / C::TX;
+      const int kx = k0 + cc;
+      if (kx < nxh) {
+        const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
+        const double x = kx * rx, y = fy * ry, z = fz * rz;
+        const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
+        const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
+        double g[6];
+        if (!nyq && !zero) green_G(c_green, x, y, z, scale, g);
+        double *smd = reinterpret_cast<double *>(sm);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          double lam[6], o[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) lam[c] = smd[2 * (c * C::CS + idx) + part];
+          if (zero) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) o[c] = 0.0;
+          } else if (nyq) {
+            green_nyquist(c_green, scale, lam, o);
+          } else {
+            green_apply(g, x, y, z, lam, o);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) smd[2 * (c * C::CS + idx) + part] = o[c];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = cg; c < 6; c += C::CG) block_fft<NZ, true>(sm, q, OffES<C::TX>{c * C::CS + col}, TwLdg{twp});
   }
-  for (int idx = tid; idx < 6 * C::CS; idx += C::T) {
-    const int cc = idx % C::TX, z = (idx / C::TX) % NZ, c = idx / C::CS;
-    if (k0 + cc < nxh) Wt[Lay.row_zsplit(c, z, yl) + k0 + cc] = sm[idx];
+  tma::fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c)
+#pragma unroll 1
+      for (int z0 = 0; z0 < NZ; z0 += zc)
+        tma::store5(&tz, sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzl) - 1), c, z0 >> lg_nzl);
+    tma::commit();
+    tma::wait_read0();
   }
 }
 
@@ -277,55 +368,71 @@ __device__ __forceinline__ int warp_max(int v) {
   return v;
 }
 
-// block reduction of NV values (sum) + one max; result written by thread 0 to out[0..NV], out[NV] = max
+// per-warp partial sums (no block barrier): lane 0 of every warp stores NV sums and one max into the
+// SoA partial buffer  partials[k * nw + warp]
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double vals[NV], int vmax, double *out) {
-  __shared__ double red[kCB / 32][NV + 1];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ void warp_partials_store(const double vals[NV], int vmax, double *__restrict__ partials, long long nw) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const double s = warp_sum(vals[k]);
-    if (lane == 0) red[w][k] = s;
+    if (lane == 0) partials[(long long)k * nw + gw] = s;
   }
   const int m = warp_max(vmax);
-  if (lane == 0) red[w][NV] = (double)m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double s = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < kCB / 32; ++ww) s += red[ww][k];
-      out[k] = s;
-    }
-    double mm = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < kCB / 32; ++ww) mm = fmax(mm, red[ww][NV]);
-    out[NV] = mm;
-  }
+  if (lane == 0) partials[(long long)NV * nw + gw] = (double)m;
 }
 
-__global__ void __launch_bounds__(kCB) k_constitutive(Fields f, double *__restrict__ partials) {
-  extern __shared__ double itc_sm[];  // [nsmax][kCB]
+struct SmAcc {      // strided per-thread array in shared memory: element k of this thread
+  double *p;
+  __device__ __forceinline__ double operator()(int k) const { return p[k * kCB]; }
+  __device__ __forceinline__ void operator()(int k, double v) const { p[k * kCB] = v; }
+};
+
+// K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
+// (tables addressed as c_phase[0], i.e. immediate constant-bank operands).
+template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
+__global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *__restrict__ partials, long long nw) {
+  extern __shared__ double smd[];  // [21 Jb | 6 g | 6 s_old | nsmax 1/tau_c] x kCB
   const int tid = threadIdx.x;
   const long long v = (long long)blockIdx.x * kCB + tid;
   const long long N = f.N;
   double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
   int nit = 0;
   if (v < N) {
-    const PhaseDev &P = c_phase[f.phase[v]];
-    double R[9], sig[6], em[6];
+    const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
+    const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
+    double sc[6];
+    {
+      double R[9], sig[6], em[6], ep[6];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = __ldg(f.rot + k * N + v);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) em[c] = f.e[c * N + v];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) ep[c] = __ldg(f.epsp + c * N + v);
+      const int ns = (NS_T > 0) ? NS_T : P.nsys;
+      if (NS_T > 0) {
+        double tc[NS_T > 0 ? NS_T : 1];
+#pragma unroll
+        for (int s = 0; s < NS_T; ++s) tc[s] = __ldg(f.crss + (long long)s * N + v);
+#pragma unroll
+        for (int s = 0; s < NS_T; ++s) itc(s, 1.0 / tc[s]);
+      } else {
+        for (int s = 0; s < ns; ++s) itc(s, 1.0 / __ldg(f.crss + (long long)s * N + v));
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) em[c] -= ep[c];
+      constitutive_prep(P, c_cp, R, sig, em, jb, gv, so, sc);
+    }
+    int bad = 0;
+    nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
+    double R[9], sig[6], ds, de;
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = __ldg(f.rot + k * N + v);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) em[c] = f.e[c * N + v] - __ldg(f.epsp + c * N + v);
-    const int ns = P.nsys;
-    for (int s = 0; s < ns; ++s) itc_sm[s * kCB + tid] = 1.0 / __ldg(f.crss + (long long)s * N + v);
-    int bad = 0;
-    double ds, de;
-    nit = constitutive_voxel(P, c_cp, R, sig, em, ItcSmem{itc_sm + tid}, &ds, &de, &bad);
+    constitutive_finish(P, R, sc, jb, so, sig, &ds, &de);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       f.sig[c * N + v] = sig[c];
@@ -336,33 +443,35 @@ __global__ void __launch_bounds__(kCB) k_constitutive(Fields f, double *__restri
     vals[8] = (double)nit;
     vals[9] = (double)bad;
   }
-  block_reduce_store<10>(vals, nit, partials + (long long)blockIdx.x * kPartial);
+  warp_partials_store<10>(vals, nit, partials, nw);
 }
 
-// second stage of the reductions: fixed-order sum of the block partials (deterministic)
-__global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ partials, int nblocks, double *__restrict__ totals) {
-  __shared__ double red[256][12];
+// second stage of the reductions: fixed-order two-level sum of the warp partials (deterministic)
+constexpr int kRedBlocks = 296;
+__global__ void __launch_bounds__(256) k_reduce1(const double *__restrict__ partials, long long nw, double *__restrict__ scratch) {
+  __shared__ double red[256];
   const int tid = threadIdx.x;
-  double acc[11];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) acc[k] = 0.0;
-  for (int b = tid; b < nblocks; b += 256) {
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] += partials[(long long)b * kPartial + k];
-    acc[10] = fmax(acc[10], partials[(long long)b * kPartial + 10]);
-  }
-#pragma unroll
-  for (int k = 0; k < 11; ++k) red[tid][k] = acc[k];
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) {
-#pragma unroll
-      for (int k = 0; k < 10; ++k) red[tid][k] += red[tid + s][k];
-      red[tid][10] = fmax(red[tid][10], red[tid + s][10]);
+  const long long chunk = (nw + gridDim.x - 1) / gridDim.x;
+  const long long w0 = (long long)blockIdx.x * chunk, w1 = (w0 + chunk < nw) ? w0 + chunk : nw;
+  for (int k = 0; k < 11; ++k) {
+    double acc = 0.0;
+    for (long long w = w0 + tid; w < w1; w += 256) acc = (k < 10) ? acc + partials[(long long)k * nw + w] : fmax(acc, partials[(long long)k * nw + w]);
+    red[tid] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (tid < s) red[tid] = (k < 10) ? red[tid] + red[tid + s] : fmax(red[tid], red[tid + s]);
+      __syncthreads();
     }
+    if (tid == 0) scratch[(long long)blockIdx.x * 16 + k] = red[0];
     __syncthreads();
   }
-  if (tid < 11) totals[tid] = red[0][tid];
+}
+__global__ void __launch_bounds__(32) k_reduce2(const double *__restrict__ scratch, int nb, double *__restrict__ totals) {
+  const int k = threadIdx.x;
+  if (k >= 11) return;
+  double acc = 0.0;
+  for (int b = 0; b < nb; ++b) acc = (k < 10) ? acc + scratch[(long long)b * 16 + k] : fmax(acc, scratch[(long long)b * 16 + k]);
+  totals[k] = acc;
 }
 
 // rows a6 (normalisation) + a7 (macro strain correction) on the device.
@@ -400,7 +509,7 @@ __device__ __forceinline__ double voce_tau(const PhaseDev &P, int m, double G) {
   return t0 + (t1 + h1 * G) * (1.0 - exp(-G * fabs(h0 / t1)));
 }
 
-__global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__restrict__ partials) {
+__global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__restrict__ partials, long long nw) {
   extern __shared__ double dg_sm[];  // [nsmax][kCB] |dgamma|
   const int tid = threadIdx.x;
   const long long v = (long long)blockIdx.x * kCB + tid;
@@ -465,7 +574,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__r
       f.gacc[v] = G0 + dG;
     }
   }
-  block_reduce_store<10>(sums, 0, partials + (long long)blockIdx.x * kPartial);
+  warp_partials_store<10>(sums, 0, partials, nw);
 }
 
 __global__ void k_fill(double *p, long long n, double v) {
@@ -485,10 +594,13 @@ __global__ void k_init_crss(Fields f, int nsmax) {
 // ---------------------------------------------------------------------------------------------
 bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
 
-template <class K>
-static void set_smem(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
+// opt in to > 48 KB dynamic shared memory, once per kernel instantiation (the call is not free)
+#define set_smem(bytes, ...)                                                                          \
+  do {                                                                                                \
+    static bool done_ = false;                                                                        \
+    if (!done_ && (bytes) > 48 * 1024) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+    done_ = true;                                                                                     \
+  } while (0)
 
 #define EVP_DISPATCH_N(n, MACRO) \
   switch (n) {                   \
@@ -508,7 +620,7 @@ void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int nrows, 
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
-    set_smem(k_xfwd<NX>, C::smem);                                                                    \
+    set_smem(C::smem, k_xfwd<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
     k_xfwd<NX><<<grid, C::T, C::smem, st>>>(sig, W, N, nrows, L, ny, tw);                              \
   }
@@ -522,7 +634,7 @@ void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const Macr
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
-    set_smem(k_xinv<NX>, C::smem);                                                                    \
+    set_smem(C::smem, k_xinv<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
     k_xinv<NX><<<grid, C::T, C::smem, st>>>(W, e, de_dbg, macro, N, nrows, L, ny, tw);                 \
   }
@@ -530,60 +642,90 @@ void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const Macr
 #undef X_
 }
 
-void launch_ypass(int ny, bool inv, const double2 *in, double2 *out, SpecLayout Lin, SpecLayout Lout, int nzl,
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzl,
                   const double2 *tw, cudaStream_t st) {
 #define Y_(NY)                                                                                        \
   {                                                                                                   \
     using C = YCfg<NY>;                                                                               \
-    dim3 grid((Lin.nxh + C::TX - 1) / C::TX, (nzl + C::ZT - 1) / C::ZT, 6);                           \
+    dim3 grid((nxh + C::TX - 1) / C::TX, (nzl + C::ZT - 1) / C::ZT, 6);                               \
     if (inv) {                                                                                        \
-      set_smem(k_ypass<NY, true>, C::smem);                                                           \
-      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(in, out, Lin, Lout, nzl, tw);                    \
+      set_smem(C::smem, k_ypass<NY, true>);                                                           \
+      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, tw); \
     } else {                                                                                          \
-      set_smem(k_ypass<NY, false>, C::smem);                                                          \
-      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(in, out, Lin, Lout, nzl, tw);                   \
+      set_smem(C::smem, k_ypass<NY, false>);                                                          \
+      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(ny, Y_)
 #undef Y_
 }
 
-void launch_zfused(int nz, bool fwd_only, double2 *Wt, SpecLayout L, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz,
-                   const double2 *tw, cudaStream_t st) {
+void launch_zfused(int nz, bool fwd_only, const CUtensorMap &tz, TileInfo zi, int nxh, int nyl, int ky0, int nx, int ny, double dx,
+                   double dy, double dz, const double2 *tw, cudaStream_t st) {
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
 #define Z_(NZ)                                                                                        \
   {                                                                                                   \
     using C = ZCfg<NZ>;                                                                               \
-    dim3 grid((L.nxh + C::TX - 1) / C::TX, nyl);                                                      \
+    dim3 grid((nxh + C::TX - 1) / C::TX, nyl);                                                        \
     if (fwd_only) {                                                                                   \
-      set_smem(k_zfused<NZ, 1>, C::smem);                                                             \
-      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(Wt, L, ky0, nx, ny, rx, ry, rz, scale, tw);        \
+      set_smem(C::smem, k_zfused<NZ, 1>);                                                             \
+      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, zi.lg, zi.chunk, ky0, nx, ny, rx, ry, rz, scale, tw); \
     } else {                                                                                          \
-      set_smem(k_zfused<NZ, 0>, C::smem);                                                             \
-      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(Wt, L, ky0, nx, ny, rx, ry, rz, scale, tw);        \
+      set_smem(C::smem, k_zfused<NZ, 0>);                                                             \
+      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, zi.lg, zi.chunk, ky0, nx, ny, rx, ry, rz, scale, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(nz, Z_)
 #undef Z_
 }
 
-void launch_constitutive(const Fields &f, int nsmax, double *partials, int *nblocks_out, cudaStream_t st) {
+int ypass_tx() { return 8; }
+int zpass_tx(int nz) { return (nz >= 1024) ? 2 : ((nz >= 256) ? 4 : 8); }
+
+static long long num_warps(long long N) { return ((N + kCB - 1) / kCB) * (kCB / 32); }
+long long partial_doubles(long long N) { return 11 * num_warps(N); }
+int reduce_scratch_doubles() { return kRedBlocks * 16; }
+
+template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
+static void launch_const_t(const Fields &f, int nsmax, double *partials, cudaStream_t st) {
   const int nb = (int)((f.N + kCB - 1) / kCB);
-  const size_t smem = (size_t)(nsmax > 0 ? nsmax : 1) * kCB * sizeof(double);
-  k_constitutive<<<nb, kCB, smem, st>>>(f, partials);
-  if (nblocks_out) *nblocks_out = nb;
+  const size_t smem = (size_t)(33 + (nsmax > 0 ? nsmax : 1)) * kCB * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024);
+    cudaFuncSetAttribute(k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+  k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, partials, num_warps(f.N));
 }
 
-void launch_commit(const Fields &f, int nsmax, double dt, double *partials, int *nblocks_out, cudaStream_t st) {
-  const int nb = (int)((f.N + kCB - 1) / kCB);
-  const size_t smem = (size_t)(nsmax > 0 ? nsmax : 1) * kCB * sizeof(double);
-  k_commit<<<nb, kCB, smem, st>>>(f, dt, partials);
-  if (nblocks_out) *nblocks_out = nb;
+// variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
+void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st) {
+  const bool one = nphases == 1;
+  static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 4;   // tuning knob: resident blocks per SM
+  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 3) return launch_const_t<12, 9, true, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 2) return launch_const_t<12, 9, true, 2>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 4>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 4>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 4>(f, nsmax, partials, st);
+  if (one && uniform_ns == 24 && uniform_npow == 9) return launch_const_t<24, 9, true, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 24 && uniform_npow == 19) return launch_const_t<24, 19, true, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 24) return launch_const_t<24, -2, true, 3>(f, nsmax, partials, st);
+  return launch_const_t<0, -2, false, 3>(f, nsmax, partials, st);
 }
 
-void launch_reduce(const double *partials, int nblocks, double *totals, cudaStream_t st) {
-  k_reduce<<<1, 256, 0, st>>>(partials, nblocks, totals);
+void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st) {
+  const int nb = (int)((f.N + kCB - 1) / kCB);
+  const size_t smem = (size_t)(nsmax > 0 ? nsmax : 1) * kCB * sizeof(double);
+  k_commit<<<nb, kCB, smem, st>>>(f, dt, partials, num_warps(f.N));
+}
+
+void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) {
+  const long long nw = num_warps(N);
+  const int nb = (int)((nw < kRedBlocks) ? nw : kRedBlocks);
+  k_reduce1<<<nb, 256, 0, st>>>(partials, nw, scratch);
+  k_reduce2<<<1, 32, 0, st>>>(scratch, nb, totals);
 }
 void launch_macro(const double *totals, MacroDev *macro, double ntot, cudaStream_t st) { k_macro<<<1, 32, 0, st>>>(totals, macro, ntot); }
 void launch_fill(double *p, long long n, double v, cudaStream_t st) { k_fill<<<592, 256, 0, st>>>(p, n, v); }

@@ -10,6 +10,7 @@
 // Reference counterpart: absent (mount holds only LICENSE); units per SURVEY.md §8(a).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "evp_core.h"
@@ -25,12 +26,13 @@ namespace evp {
 // ---------------------------------------------------------------------------------------------
 struct SpecLayout {
   int nyl, nzl, nxp, nxh;
+  int lg_nyl, lg_nzl;          // all extents are powers of two: divisions become shifts
   long long cstride, zstride, dstride;
   __host__ __device__ long long row_ysplit(int c, int zl, int y) const {
-    return (long long)(y / nyl) * dstride + (long long)c * cstride + (long long)zl * zstride + (long long)(y % nyl) * nxp;
+    return (long long)(y >> lg_nyl) * dstride + (long long)c * cstride + (long long)zl * zstride + (long long)(y & (nyl - 1)) * nxp;
   }
   __host__ __device__ long long row_zsplit(int c, int z, int yl) const {
-    return (long long)(z / nzl) * dstride + (long long)c * cstride + (long long)(z % nzl) * zstride + (long long)yl * nxp;
+    return (long long)(z >> lg_nzl) * dstride + (long long)c * cstride + (long long)(z & (nzl - 1)) * zstride + (long long)yl * nxp;
   }
 };
 
@@ -49,7 +51,6 @@ struct Fields {
   long long N;              // local voxels; component stride of every SoA field
 };
 
-constexpr int kPartial = 16;  // doubles per block partial: ds, de, sig[6], nit_sum, nit_max, bad, epsp[6]->(commit reuses 2..7)
 
 void upload_phase_tables(const PhaseDev *ph, int nph);
 void upload_green(const GreenConst &g);
@@ -57,16 +58,22 @@ void upload_const_params(const ConstParams &p);
 
 // launches (all on `st`)
 void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int nrows, SpecLayout L, const double2 *tw, cudaStream_t st);
-void launch_ypass(int ny, bool inv, const double2 *in, double2 *out, SpecLayout Lin, SpecLayout Lout, int nzl, const double2 *tw,
-                  cudaStream_t st);
-void launch_zfused(int nz, bool fwd_only, double2 *Wt, SpecLayout L, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz,
-                   const double2 *tw, cudaStream_t st);
+// TMA tiling of one spectral-buffer view: rows (y or z) per op and log2 of the rows per rank chunk
+struct TileInfo { int lg, chunk; };
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzl,
+                  const double2 *tw, cudaStream_t st);
+void launch_zfused(int nz, bool fwd_only, const CUtensorMap &tz, TileInfo zi, int nxh, int nyl, int ky0, int nx, int ny, double dx,
+                   double dy, double dz, const double2 *tw, cudaStream_t st);
+int ypass_tx();
+int zpass_tx(int nz);
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int nrows, SpecLayout L,
                  const double2 *tw, cudaStream_t st);
-void launch_constitutive(const Fields &f, int nsmax, double *partials, int *nblocks_out, cudaStream_t st);
-void launch_reduce(const double *partials, int nblocks, double *totals, cudaStream_t st);
+void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st);
+void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st);
+long long partial_doubles(long long N);
+int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
-void launch_commit(const Fields &f, int nsmax, double dt, double *partials, int *nblocks_out, cudaStream_t st);
+void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st);
 void launch_fill(double *p, long long n, double v, cudaStream_t st);
 void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st);
 bool fft_size_supported(int n);

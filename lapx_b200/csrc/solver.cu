@@ -2,6 +2,8 @@
 // sm_100a kernels (kernels.cu).  There is NO CPU fallback here: without an sm_100 device
 // evp_create fails with EVP_ERR_DEVICE.
 // Reference counterpart: absent (/root/reference holds only LICENSE); ABI per SURVEY.md §8(b).
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -83,14 +85,16 @@ struct evp_solver {
   double2 *WA = nullptr, *WB = nullptr;
   double2 *twx = nullptr, *twy = nullptr, *twz = nullptr;
   MacroDev *d_macro = nullptr, *h_macro = nullptr;  // h_macro pinned
-  double *d_partials = nullptr, *d_totals = nullptr;
-  int nblocks = 0;
+  double *d_partials = nullptr, *d_totals = nullptr, *d_scratch = nullptr;
+  int uniform_ns = 0, uniform_npow = -2;
   SpecLayout Lplain{}, Lsplit{};
+  CUtensorMap tm_y_plain{}, tm_y_split{}, tm_z{};   // TMA descriptors of the spectral buffers
+  TileInfo ti_y_plain{}, ti_y_split{}, ti_z{};
   double C0m[36]{}, S0m[36]{};
   ConstParams cp{};
   GreenConst green{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
-  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-9, 100};
+  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100};
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};
   bool strain_ctl[6]{};
@@ -115,6 +119,33 @@ int fail(evp_handle h, int code, const std::string &m) {
     cudaError_t e_ = (call);                                                                      \
     if (e_ != cudaSuccess) return fail(h, EVP_ERR_DEVICE, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+int ilog2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// 5-D tensor [2*nxp doubles][nyl][nzl][6][P] over a spectral buffer; box = [2*tx][box_y][box_z][1][1]
+bool make_tmap(CUtensorMap *m, void *base, const SpecLayout &L, int P, int tx, int box_y, int box_z, std::string *err) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      *err = "cuTensorMapEncodeTiled entry point not available";
+      return false;
+    }
+    encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  const cuuint64_t dims[5] = {(cuuint64_t)2 * L.nxp, (cuuint64_t)L.nyl, (cuuint64_t)L.nzl, 6, (cuuint64_t)P};
+  const cuuint64_t strides[4] = {(cuuint64_t)L.nxp * 16, (cuuint64_t)L.zstride * 16, (cuuint64_t)L.cstride * 16, (cuuint64_t)L.dstride * 16};
+  const cuuint32_t box[5] = {(cuuint32_t)2 * tx, (cuuint32_t)box_y, (cuuint32_t)box_z, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
 
 double2 *make_twiddles(int n) {
   std::vector<double2> t(n);
@@ -183,23 +214,21 @@ int enqueue_green(evp_handle h) {
   rec(h, 0);
   launch_xfwd(h->nx, h->f.sig, h->WB, h->N, nrows, h->Lplain, h->twx, h->st);
   rec(h, 1);
-  launch_ypass(h->ny, false, h->WB, h->WA, h->Lplain, h->Lsplit, h->nzl, h->twy, h->st);
+  launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_split, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzl, h->twy, h->st);
   rec(h, 2);
-  double2 *Wz = h->WA;
   if (h->nranks > 1) {
     int rc = all_to_all(h, h->WA, h->WB);
     if (rc) return rc;
-    Wz = h->WB;
   }
   rec(h, 3);
-  launch_zfused(h->nz, false, Wz, h->Lsplit, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_zfused(h->nz, false, h->tm_z, h->ti_z, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   rec(h, 4);
   if (h->nranks > 1) {
     int rc = all_to_all(h, h->WB, h->WA);
     if (rc) return rc;
   }
   rec(h, 5);
-  launch_ypass(h->ny, true, h->WA, h->WB, h->Lsplit, h->Lplain, h->nzl, h->twy, h->st);
+  launch_ypass(h->ny, true, h->tm_y_split, h->tm_y_plain, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
   rec(h, 6);
   launch_xinv(h->nx, h->WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, nrows, h->Lplain, h->twx, h->st);
   rec(h, 7);
@@ -208,8 +237,8 @@ int enqueue_green(evp_handle h) {
 
 // rows a4+a5+a6+a7
 int enqueue_constitutive(evp_handle h) {
-  launch_constitutive(h->f, h->nsmax, h->d_partials, &h->nblocks, h->st);
-  launch_reduce(h->d_partials, h->nblocks, h->d_totals, h->st);
+  launch_constitutive(h->f, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->d_partials, h->st);
+  launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals, h->st);
   if (h->nranks > 1) {
     int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, h->comm, h->st);
     if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, h->comm, h->st);
@@ -319,6 +348,13 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
     }
     build_phase_dev(phases[p], S->phd[p]);
     S->nsmax = std::max(S->nsmax, (int)phases[p].nsys);
+    for (int q = 0; q < phases[p].nsys; ++q) {
+      const int np = S->phd[p].npow[q];
+      if (p == 0 && q == 0) S->uniform_npow = np;
+      else if (np != S->uniform_npow) S->uniform_npow = -2;
+    }
+    if (p == 0) S->uniform_ns = phases[p].nsys;
+    else if (phases[p].nsys != S->uniform_ns) S->uniform_ns = 0;
     for (int m = 0; m < phases[p].nmodes; ++m) any_twin |= phases[p].twin[m] != 0;
   }
 #define CK(call)                                                                                   \
@@ -362,15 +398,32 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   S->Lsplit.zstride = (long long)S->nyl * S->nxp;
   S->Lsplit.cstride = (long long)S->nzl * S->Lsplit.zstride;
   S->Lsplit.dstride = 6 * S->Lsplit.cstride;
+  S->Lplain.lg_nyl = ilog2i(S->ny); S->Lplain.lg_nzl = ilog2i(S->nzl);
+  S->Lsplit.lg_nyl = ilog2i(S->nyl); S->Lsplit.lg_nzl = ilog2i(S->nzl);
+  {
+    std::string e;
+    const int ycp = std::min(S->ny, 256), ycs = std::min(S->nyl, 256), zc = std::min(S->nzl, 256);
+    S->ti_y_plain = {S->Lplain.lg_nyl, ycp};
+    S->ti_y_split = {S->Lsplit.lg_nyl, ycs};
+    S->ti_z = {S->Lsplit.lg_nzl, zc};
+    // K2 -> WB (plain) -> K3 -> WA (split) -> [all-to-all -> WB] -> K4 -> [all-to-all -> WA] -> K5 -> WB (plain) -> K6
+    double2 *Wz = (nranks > 1) ? S->WB : S->WA;
+    if (!make_tmap(&S->tm_y_plain, S->WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) ||
+        !make_tmap(&S->tm_y_split, S->WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) ||
+        !make_tmap(&S->tm_z, Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, zc, &e)) {
+      evp_destroy(S);
+      return fail(nullptr, EVP_ERR_DEVICE, e);
+    }
+  }
   S->twx = make_twiddles(S->nx); S->twy = make_twiddles(S->ny); S->twz = make_twiddles(S->nz);
   if (!S->twx || !S->twy || !S->twz) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "twiddle allocation failed"); }
   CK(cudaMalloc(&S->d_macro, sizeof(MacroDev)));
   CK(cudaMemset(S->d_macro, 0, sizeof(MacroDev)));
   CK(cudaMallocHost(&S->h_macro, sizeof(MacroDev)));
   std::memset(S->h_macro, 0, sizeof(MacroDev));
-  const int nb = (int)((N + constitutive_block() - 1) / constitutive_block());
-  CK(cudaMalloc(&S->d_partials, sizeof(double) * kPartial * (size_t)nb));
+  CK(cudaMalloc(&S->d_partials, sizeof(double) * (size_t)partial_doubles(N)));
   CK(cudaMalloc(&S->d_totals, sizeof(double) * 64));
+  CK(cudaMalloc(&S->d_scratch, sizeof(double) * reduce_scratch_doubles()));
   if (nranks > 1) {
     std::string e;
     if (!load_nccl(&e)) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, e); }
@@ -397,7 +450,7 @@ int evp_destroy(evp_handle h) {
   if (h->WB && h->WB != h->WA) cudaFree(h->WB);
   cudaFree(h->WA);
   cudaFree(h->twx); cudaFree(h->twy); cudaFree(h->twz);
-  cudaFree(h->d_macro); cudaFree(h->d_partials); cudaFree(h->d_totals);
+  cudaFree(h->d_macro); cudaFree(h->d_partials); cudaFree(h->d_totals); cudaFree(h->d_scratch);
   if (h->h_macro) cudaFreeHost(h->h_macro);
   if (h->ev_made) for (auto &e : h->ev) cudaEventDestroy(e);
   if (h->st) cudaStreamDestroy(h->st);
@@ -633,9 +686,8 @@ int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
 int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "end_increment outside an increment");
   activate(h);
-  int nb = 0;
-  launch_commit(h->f, h->nsmax, h->dt, h->d_partials, &nb, h->st);
-  launch_reduce(h->d_partials, nb, h->d_totals + 16, h->st);
+  launch_commit(h->f, h->nsmax, h->dt, h->d_partials, h->st);
+  launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals + 16, h->st);
   if (h->nranks > 1) {
     int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 10, kNcclDouble, kNcclSum, h->comm, h->st);
     if (rc) return nccl_check(h, rc, "nccl allreduce (commit)");
@@ -731,8 +783,8 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   if (h->nranks != 1) return fail(h, EVP_ERR_UNSUPPORTED, "debug_spectrum: single-rank handles only");
   activate(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, h->ny * h->nzl, h->Lplain, h->twx, h->st);
-  launch_ypass(h->ny, false, h->WA, h->WA, h->Lplain, h->Lplain, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, true, h->WA, h->Lplain, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
+  launch_zfused(h->nz, true, h->tm_z, h->ti_z, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

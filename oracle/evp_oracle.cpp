@@ -235,7 +235,7 @@ struct evp_solver {
   std::vector<double> rot, sig, e, epsp, edotp, crss, gacc, twinf, de;
   double C0[36]{}, S0[36]{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
-  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-9, 100};
+  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100};
   // loading
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};

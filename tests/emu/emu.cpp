@@ -42,6 +42,24 @@ struct ItcArr { const double *p; double operator()(int s) const { return p[s]; }
 
 }  // namespace
 
+namespace {
+struct ArrAcc {
+  double *p;
+  double operator()(int k) const { return p[k]; }
+  void operator()(int k, double v) const { p[k] = v; }
+};
+template <int NS_T, int NPOW_T>
+int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig, const double *em, double *itc, double *ds, double *de,
+          int *bad) {
+  double jb[21], g[6], so[6], sc[6];
+  constitutive_prep(P, cp, R, sig, em, ArrAcc{jb}, ArrAcc{g}, ArrAcc{so}, sc);
+  const int nit = newton_crystal_t<NS_T, NPOW_T>(P, ArrAcc{jb}, ArrAcc{g}, sc, cp.dt, cp.tol_newton, cp.newton_itmax, ArrAcc{itc}, bad);
+  constitutive_finish(P, R, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
+  return nit;
+}
+}  // namespace
+
+
 extern "C" {
 
 // in-place FFT of nlines contiguous lines of length n (interleaved re,im); same pass sequence as block_fft
@@ -91,5 +109,31 @@ int emu_green_point(const double *c0_voigt, double x, double y, double z, int ze
 }
 
 int emu_rot_b5(const double *R, double *M) { rot_b5(R, M); return 0; }
+
+// production (templated) form of k_constitutive_t: variant 0 = generic, 1 = <12,9>, 2 = <12,-2>, 3 = <24,9>, 4 = <12,19>, 5 = <24,19>, 6 = <24,-2>
+int emu_constitutive_t(int variant, const evp_phase *ph, const double *c0_voigt, const double *R, double *sig, const double *e,
+                       const double *epsp, const double *crss, double dt, double tol, int itmax, double *ds, double *de, int *bad) {
+  PhaseDev P;
+  build_phase_dev(*ph, P);
+  double C0m[36], S0m[36];
+  voigt_to_mandel(c0_voigt, C0m);
+  inv6(C0m, S0m);
+  ConstParams cp;
+  build_s0b(S0m, cp.S0b, &cp.iso_c0);
+  cp.dt = dt; cp.tol_newton = tol; cp.newton_itmax = itmax;
+  double itc[EVP_MAX_SYS], em[6];
+  for (int s = 0; s < ph->nsys; ++s) itc[s] = 1.0 / crss[s];
+  for (int c = 0; c < 6; ++c) em[c] = e[c] - epsp[c];
+  *bad = 0;
+  switch (variant) {
+    case 1: return run_t<12, 9>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 2: return run_t<12, -2>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 3: return run_t<24, 9>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 4: return run_t<12, 19>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 5: return run_t<24, 19>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 6: return run_t<24, -2>(P, cp, R, sig, em, itc, ds, de, bad);
+    default: return run_t<0, -2>(P, cp, R, sig, em, itc, ds, de, bad);
+  }
+}
 
 }  // extern "C"

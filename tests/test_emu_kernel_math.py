@@ -116,12 +116,13 @@ def test_green_point_matches_tensor_formula(emu, product_lib):
     assert np.all(out == 0)
 
 
-@pytest.mark.parametrize("hcp", [False, True])
+@pytest.mark.parametrize("hcp,nrate,variants", [(False, 10.0, [0, 1, 2]), (True, 10.0, [0, 3, 6]), (False, 20.0, [0, 2, 4]),
+                                                 (True, 20.0, [5]), (False, 7.5, [0, 2])])
 @pytest.mark.parametrize("iso", [False, True])
-def test_constitutive_voxel_matches_sample_frame_newton(emu, product_lib, hcp, iso):
+def test_constitutive_voxel_matches_sample_frame_newton(emu, product_lib, hcp, nrate, variants, iso):
     """Crystal-frame b-basis LDL^T Newton (kernel math) vs a sample-frame Mandel Newton in numpy."""
-    rng = np.random.default_rng(11 + hcp + 2 * iso)
-    ph = ms.hcp_phase(product_lib, with_twin=1) if hcp else ms.fcc_phase(product_lib)
+    rng = np.random.default_rng(11 + hcp + 2 * iso + int(nrate))
+    ph = ms.hcp_phase(product_lib, with_twin=1, nrate=nrate) if hcp else ms.fcc_phase(product_lib, nrate=nrate)
     if iso:
         K, mu = 140000.0, 48000.0
         c0 = np.zeros((6, 6))
@@ -142,6 +143,7 @@ def test_constitutive_voxel_matches_sample_frame_newton(emu, product_lib, hcp, i
     g0 = np.array([ph.gamma0[m] for m in mode])
     cv = np.array(list(ph.c_voigt)).reshape(6, 6)
     emu.emu_constitutive.argtypes = [C.c_void_p] * 7 + [C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    emu.emu_constitutive_t.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 3
     for trial in range(25):
         R = _rand_rot(rng)
         Cs = np.einsum("ia,jb,kc,ld,abcd->ijkl", R, R, R, R, _c4(cv))
@@ -182,6 +184,16 @@ def test_constitutive_voxel_matches_sample_frame_newton(emu, product_lib, hcp, i
         assert np.abs(sig - ref).max() < 1e-9 * np.abs(ref).max(), (trial, sig, ref)
         assert abs(ds.value - np.linalg.norm(s - so_m)) < 1e-9 * np.linalg.norm(s - so_m)
         assert abs(de.value - np.linalg.norm(S0m @ (s - so_m))) < 1e-9 * np.linalg.norm(S0m @ (s - so_m))
+        for var in variants:   # production (templated / unrolled) kernel variants
+            sig3 = np.ascontiguousarray(so.copy())
+            nit3 = emu.emu_constitutive_t(var, C.byref(ph), c0.ctypes.data_as(C.c_void_p), Rc.ctypes.data_as(C.c_void_p),
+                                          sig3.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                          ep.ctypes.data_as(C.c_void_p), crss.ctypes.data_as(C.c_void_p), dt, 1e-12, 200,
+                                          C.byref(ds), C.byref(de), C.byref(bad))
+            assert bad.value == 0 and nit3 == nit, (var, nit3, nit)
+            assert np.abs(sig3 - ref).max() < 1e-9 * np.abs(ref).max(), var
+            assert abs(ds.value - np.linalg.norm(s - so_m)) < 1e-9 * np.linalg.norm(s - so_m)
+            assert abs(de.value - np.linalg.norm(S0m @ (s - so_m))) < 1e-9 * np.linalg.norm(S0m @ (s - so_m))
         if iso:  # the general (rotated S0) path must agree with the isotropic fast path
             sig2 = np.ascontiguousarray(so.copy())
             emu.emu_constitutive(C.byref(ph), c0.ctypes.data_as(C.c_void_p), Rc.ctypes.data_as(C.c_void_p),
