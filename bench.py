@@ -37,6 +37,7 @@ METRIC = "voxel-updates/s per equilibrium iter (fp64)"
 UNIT = "voxel-updates/s"
 GRIDS = {1: (256, 256, 256), 2: (256, 256, 512), 4: (256, 512, 512), 8: (512, 512, 512)}
 DT = 2e-4
+PRE_ITERS = 10    # untimed iterations before the warm-up: the timed ones are mid-increment
 TOL_NEWTON = float(os.environ.get("EVP_TOL_NEWTON", "1e-6"))   # library default; accepted iterate is accurate to ~tol^2
 
 
@@ -214,14 +215,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as td
+        from lapx_b200 import distributed as evd
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf = (api.C.c_uint8 * 128)()
-            assert lib.evp_nccl_unique_id(buf) == 0
-            idt.copy_(torch.tensor(list(buf), dtype=torch.uint8))
-        td.broadcast(idt, 0)
-        dist = api.Dist(world, rank, local, 0, (api.C.c_uint8 * 128)(*idt.cpu().tolist()))
+        dist = evd.make_dist(lib, world, rank, local, td)
     ngrains = 10000 if grid == (512, 512, 512) else max(50, int(round(grid[0] * grid[1] * grid[2] / 16777.216)))
     s, ld, nsys, t_up, up_bytes = build_solver(lib, lib, grid, ngrains, args.workload, dist=dist)
     N = grid[0] * grid[1] * grid[2]
@@ -235,8 +231,9 @@ def main():
 
     s.begin_increment(DT)
     clocks = ClockSampler(local)
-    # get out of the cold first iterations (Newton needs ~15 updates from sigma = 0), then W warm-ups
-    s.equilibrium_iters(3)
+    # get out of the cold start of the increment (Newton needs ~15 updates from sigma = 0 and the first
+    # iterations are not representative of the bulk of an increment), then W warm-ups
+    s.equilibrium_iters(PRE_ITERS)
     s.equilibrium_iters(args.warmup)
 
     # ---- device-timed value: K iterations back to back, inputs resident in HBM ----

@@ -418,15 +418,27 @@ EVP_HD int constitutive_voxel(const PhaseDev &P, const ConstParams &cp, const do
 }
 
 
-// Production split of constitutive_voxel: `prep` fills Jb (21), g (6), s_old (6) through the
-// store functors (shared memory in the kernel) and returns the crystal-frame initial guess in sc;
-// `finish` turns the converged crystal-frame stress into the sample-frame Cartesian stress and the
-// two norm contributions.  The rotation M is recomputed in finish to keep registers low.
-template <class STJ, class STG, class STS>
-EVP_HD void constitutive_prep(const PhaseDev &P, const ConstParams &cp, const double R[9], const double sig[6], const double em[6],
-                              STJ stJ, STG stG, STS stS, double sc[6]) {
-  double M[25];
+// Production split of constitutive_voxel.
+//  increment_invariants : per voxel, once per increment — the deviatoric rotation M (25) and the
+//                         packed Jb = S0_c + S_c (21); both depend only on the lattice orientation,
+//                         which is constant within an increment.
+//  constitutive_prep    : g = M^T (S0:sig_old + e - eps_p), initial guess, s_old (stored through functors)
+//  constitutive_finish  : norms + rotation of the converged crystal-frame stress back to the sample frame
+EVP_HD void increment_invariants(const PhaseDev &P, const ConstParams &cp, const double R[9], double M[25], double Jb[21]) {
   rot_b5(R, M);
+  if (cp.iso_c0) {
+#pragma unroll
+    for (int k = 0; k < 21; ++k) Jb[k] = cp.S0b[k] + P.Sc[k];
+  } else {
+    rotate_s0(cp.S0b, M, Jb);
+#pragma unroll
+    for (int k = 0; k < 21; ++k) Jb[k] += P.Sc[k];
+  }
+}
+
+template <class STG, class STS>
+EVP_HD void constitutive_prep(const ConstParams &cp, const double M[25], const double sig[6], const double em[6], STG stG, STS stS,
+                              double sc[6]) {
   double so[6], eb[6];
   cart_to_b(sig, so);
   cart_to_b(em, eb);
@@ -453,19 +465,10 @@ EVP_HD void constitutive_prep(const PhaseDev &P, const ConstParams &cp, const do
   sc[5] = so[5];
 #pragma unroll
   for (int a = 0; a < 6; ++a) stS(a, sc[a]);
-  if (cp.iso_c0) {
-#pragma unroll
-    for (int k = 0; k < 21; ++k) stJ(k, cp.S0b[k] + P.Sc[k]);
-  } else {
-    double Jb[21];
-    rotate_s0(cp.S0b, M, Jb);
-#pragma unroll
-    for (int k = 0; k < 21; ++k) stJ(k, Jb[k] + P.Sc[k]);
-  }
 }
 
 template <class JB, class SV>
-EVP_HD void constitutive_finish(const PhaseDev &P, const double R[9], const double sc[6], JB Jb, SV sold, double sig[6], double *ds,
+EVP_HD void constitutive_finish(const PhaseDev &P, const double M[25], const double sc[6], JB Jb, SV sold, double sig[6], double *ds,
                                 double *de) {
   double d[6], ds2 = 0.0, de2 = 0.0, acc[6];
 #pragma unroll
@@ -486,8 +489,7 @@ EVP_HD void constitutive_finish(const PhaseDev &P, const double R[9], const doub
   for (int a = 0; a < 6; ++a) de2 += acc[a] * acc[a];
   *ds = sqrt(ds2);
   *de = sqrt(de2);
-  double M[25], sb[6];
-  rot_b5(R, M);
+  double sb[6];
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
     double x = 0.0;

@@ -389,6 +389,23 @@ struct SmAcc {      // strided per-thread array in shared memory: element k of t
   __device__ __forceinline__ void operator()(int k, double v) const { p[k * kCB] = v; }
 };
 
+// once per increment: orientation-dependent invariants of every voxel (M, Jb) and 1/tau_c
+__global__ void __launch_bounds__(kCB) k_prep_increment(Fields f, int nsmax) {
+  const long long v = (long long)blockIdx.x * kCB + threadIdx.x;
+  const long long N = f.N;
+  if (v >= N) return;
+  const PhaseDev &P = c_phase[f.phase[v]];
+  double R[9], M[25], Jb[21];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = f.rot[k * N + v];
+  increment_invariants(P, c_cp, R, M, Jb);
+#pragma unroll
+  for (int k = 0; k < 25; ++k) f.mrot[k * N + v] = M[k];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) f.jb[k * N + v] = Jb[k];
+  for (int s = 0; s < nsmax; ++s) f.itc[(long long)s * N + v] = 1.0 / f.crss[(long long)s * N + v];
+}
+
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
 // (tables addressed as c_phase[0], i.e. immediate constant-bank operands).
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
@@ -404,35 +421,40 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
     const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
     double sc[6];
     {
-      double R[9], sig[6], em[6], ep[6];
+      // every load of the voxel is issued before the first use (39+ independent loads in flight)
+      double M[25], sig[6], em[6], ep[6], jbv[21];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = __ldg(f.rot + k * N + v);
+      for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * N + v);
 #pragma unroll
       for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
 #pragma unroll
       for (int c = 0; c < 6; ++c) em[c] = f.e[c * N + v];
 #pragma unroll
       for (int c = 0; c < 6; ++c) ep[c] = __ldg(f.epsp + c * N + v);
+#pragma unroll
+      for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * N + v);
       const int ns = (NS_T > 0) ? NS_T : P.nsys;
       if (NS_T > 0) {
         double tc[NS_T > 0 ? NS_T : 1];
 #pragma unroll
-        for (int s = 0; s < NS_T; ++s) tc[s] = __ldg(f.crss + (long long)s * N + v);
+        for (int s = 0; s < NS_T; ++s) tc[s] = __ldg(f.itc + (long long)s * N + v);
 #pragma unroll
-        for (int s = 0; s < NS_T; ++s) itc(s, 1.0 / tc[s]);
+        for (int s = 0; s < NS_T; ++s) itc(s, tc[s]);
       } else {
-        for (int s = 0; s < ns; ++s) itc(s, 1.0 / __ldg(f.crss + (long long)s * N + v));
+        for (int s = 0; s < ns; ++s) itc(s, __ldg(f.itc + (long long)s * N + v));
       }
 #pragma unroll
+      for (int k = 0; k < 21; ++k) jb(k, jbv[k]);
+#pragma unroll
       for (int c = 0; c < 6; ++c) em[c] -= ep[c];
-      constitutive_prep(P, c_cp, R, sig, em, jb, gv, so, sc);
+      constitutive_prep(c_cp, M, sig, em, gv, so, sc);
     }
     int bad = 0;
     nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
-    double R[9], sig[6], ds, de;
+    double M[25], sig[6], ds, de;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = __ldg(f.rot + k * N + v);
-    constitutive_finish(P, R, sc, jb, so, sig, &ds, &de);
+    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * N + v);   // second touch: L1/L2 hit
+    constitutive_finish(P, M, sc, jb, so, sig, &ds, &de);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       f.sig[c * N + v] = sig[c];
@@ -594,11 +616,11 @@ __global__ void k_init_crss(Fields f, int nsmax) {
 // ---------------------------------------------------------------------------------------------
 bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
 
-// opt in to > 48 KB dynamic shared memory, once per kernel instantiation (the call is not free)
+// opt in to large dynamic shared memory (static + dynamic > 48 KB), once per kernel instantiation (the call is not free)
 #define set_smem(bytes, ...)                                                                          \
   do {                                                                                                \
     static bool done_ = false;                                                                        \
-    if (!done_ && (bytes) > 48 * 1024) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+    if (!done_ && (bytes) > 40 * 1024) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
     done_ = true;                                                                                     \
   } while (0)
 
@@ -703,16 +725,21 @@ static void launch_const_t(const Fields &f, int nsmax, double *partials, cudaStr
 // variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
 void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
-  static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 4;   // tuning knob: resident blocks per SM
-  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 3) return launch_const_t<12, 9, true, 3>(f, nsmax, partials, st);
+  static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 3;   // tuning knob: resident blocks per SM
+  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 4) return launch_const_t<12, 9, true, 4>(f, nsmax, partials, st);
   if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 2) return launch_const_t<12, 9, true, 2>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 4>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 4>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 4>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 3>(f, nsmax, partials, st);
   if (one && uniform_ns == 24 && uniform_npow == 9) return launch_const_t<24, 9, true, 3>(f, nsmax, partials, st);
   if (one && uniform_ns == 24 && uniform_npow == 19) return launch_const_t<24, 19, true, 3>(f, nsmax, partials, st);
   if (one && uniform_ns == 24) return launch_const_t<24, -2, true, 3>(f, nsmax, partials, st);
   return launch_const_t<0, -2, false, 3>(f, nsmax, partials, st);
+}
+
+void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st) {
+  const int nb = (int)((f.N + kCB - 1) / kCB);
+  k_prep_increment<<<nb, kCB, 0, st>>>(f, nsmax);
 }
 
 void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st) {

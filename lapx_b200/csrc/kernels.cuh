@@ -47,6 +47,7 @@ struct MacroDev {
 
 struct Fields {
   double *sig, *e, *epsp, *edotp, *crss, *rot, *gacc, *twinf, *de;
+  double *mrot, *jb, *itc;  // per-increment invariants: deviatoric rotation M (25), Jb = S0_c + S_c (21), 1/tau_c
   int32_t *grain, *phase;
   long long N;              // local voxels; component stride of every SoA field
 };
@@ -73,6 +74,7 @@ void launch_reduce(const double *partials, long long N, double *scratch, double 
 long long partial_doubles(long long N);
 int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
+void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st);
 void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st);
 void launch_fill(double *p, long long n, double v, cudaStream_t st);
 void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st);

@@ -377,6 +377,9 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   CK(cudaMalloc(&S->f.crss, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.rot, sizeof(double) * 9 * N));
   CK(cudaMalloc(&S->f.gacc, sizeof(double) * N));
+  CK(cudaMalloc(&S->f.mrot, sizeof(double) * 25 * N));
+  CK(cudaMalloc(&S->f.jb, sizeof(double) * 21 * N));
+  CK(cudaMalloc(&S->f.itc, sizeof(double) * ns * N));
   if (any_twin) CK(cudaMalloc(&S->f.twinf, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.grain, sizeof(int32_t) * N));
   CK(cudaMalloc(&S->f.phase, sizeof(int32_t) * N));
@@ -446,6 +449,7 @@ int evp_destroy(evp_handle h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
+  cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc);
   cudaFree(h->f.rot); cudaFree(h->f.gacc); cudaFree(h->f.twinf); cudaFree(h->f.de); cudaFree(h->f.grain); cudaFree(h->f.phase);
   if (h->WB && h->WB != h->WA) cudaFree(h->WB);
   cudaFree(h->WA);
@@ -632,6 +636,7 @@ int evp_begin_increment(evp_handle h, double dt) {
     m.E[c] = h->Et[c] + m.dEpend[c];
   }
   m.iter = 0;
+  launch_prep_increment(h->f, h->nsmax, h->st);   // orientation / CRSS invariants of this increment
   CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));  // E, Et, dEpend
   CUDA_OK(h, cudaMemcpyAsync(&h->d_macro->iter, &m.iter, sizeof(int), cudaMemcpyHostToDevice, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

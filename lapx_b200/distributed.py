@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU, z-slab decomposition.
+
+torch.distributed is used only as plumbing (rendezvous + broadcasting the NCCL unique id); the FFT
+transposes are grouped ncclSend/ncclRecv all-to-alls issued by the C library itself on its stream.
+The index helpers below restate the spectral-buffer layouts of lapx_b200/csrc/kernels.cuh
+(SpecLayout) in numpy so that the decomposition logic can be tested on CPU with the gloo backend."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+
+def slab(nz: int, world: int, rank: int):
+    """z-range [z0, z0+nzl) owned by `rank` (real space) — mirrored for ky in Fourier space."""
+    if nz % world:
+        raise ValueError("nz must be divisible by the number of ranks")
+    nzl = nz // world
+    return rank * nzl, nzl
+
+
+class SpecLayout:
+    """Half-spectrum work buffer [6 comps] x [nz] x [ny] x [nxp] complex, split over `world` ranks.
+
+    y-split view (send side of the forward transpose, rows grouped by destination rank d = y // nyl):
+        addr(c, zl, y)  = (y // nyl) * dstride + c * cstride + zl * zstride + (y % nyl) * nxp
+    z-split view (receive side, planes grouped by source rank r = z // nzl):
+        addr(c, z, yl)  = (z // nzl) * dstride + c * cstride + (z % nzl) * zstride + yl * nxp
+    """
+
+    def __init__(self, nx, ny, nz, world):
+        self.nxh = nx // 2 + 1
+        self.nxp = (self.nxh + 7) // 8 * 8
+        self.nyl, self.nzl = ny // world, nz // world
+        self.zstride = self.nyl * self.nxp
+        self.cstride = self.nzl * self.zstride
+        self.dstride = 6 * self.cstride
+        self.world = world
+        self.size = world * self.dstride          # complex elements per rank
+
+    def row_ysplit(self, c, zl, y):
+        return (y // self.nyl) * self.dstride + c * self.cstride + zl * self.zstride + (y % self.nyl) * self.nxp
+
+    def row_zsplit(self, c, z, yl):
+        return (z // self.nzl) * self.dstride + c * self.cstride + (z % self.nzl) * self.zstride + yl * self.nxp
+
+
+def nccl_unique_id(lib, rank: int, broadcast_bytes) -> "C.Array":
+    """Rank 0 asks the library for an ncclUniqueId; `broadcast_bytes(np.uint8[128]) -> np.uint8[128]` ships it."""
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        rc = lib.evp_nccl_unique_id(buf)
+        if rc != 0:
+            raise api.EvpError(rc, "evp_nccl_unique_id failed")
+    arr = broadcast_bytes(np.frombuffer(buf, dtype=np.uint8).copy())
+    return (C.c_uint8 * 128)(*[int(v) for v in arr])
+
+
+def make_dist(lib, world: int, rank: int, device: int, td=None) -> api.Dist | None:
+    """Build the evp_dist argument; `td` is an initialised torch.distributed module (any backend)."""
+    if world == 1:
+        return None
+    import torch
+
+    def bcast(a):
+        use_cuda = td.get_backend() == "nccl"
+        t = torch.from_numpy(a.copy())
+        if use_cuda:
+            t = t.cuda()
+        td.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    uid = nccl_unique_id(lib, rank, bcast)
+    return api.Dist(world, rank, device, 0, uid)

@@ -51,10 +51,11 @@ struct ArrAcc {
 template <int NS_T, int NPOW_T>
 int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig, const double *em, double *itc, double *ds, double *de,
           int *bad) {
-  double jb[21], g[6], so[6], sc[6];
-  constitutive_prep(P, cp, R, sig, em, ArrAcc{jb}, ArrAcc{g}, ArrAcc{so}, sc);
+  double M[25], jb[21], g[6], so[6], sc[6];
+  increment_invariants(P, cp, R, M, jb);                       // k_prep_increment
+  constitutive_prep(cp, M, sig, em, ArrAcc{g}, ArrAcc{so}, sc);  // k_constitutive_t
   const int nit = newton_crystal_t<NS_T, NPOW_T>(P, ArrAcc{jb}, ArrAcc{g}, sc, cp.dt, cp.tol_newton, cp.newton_itmax, ArrAcc{itc}, bad);
-  constitutive_finish(P, R, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
+  constitutive_finish(P, M, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
 }  // namespace
