@@ -389,21 +389,27 @@ struct SmAcc {      // strided per-thread array in shared memory: element k of t
   __device__ __forceinline__ void operator()(int k, double v) const { p[k * kCB] = v; }
 };
 
-// once per increment: orientation-dependent invariants of every voxel (M, Jb) and 1/tau_c
-__global__ void __launch_bounds__(kCB) k_prep_increment(Fields f, int nsmax) {
-  const long long v = (long long)blockIdx.x * kCB + threadIdx.x;
-  const long long N = f.N;
-  if (v >= N) return;
+// once per increment: orientation-dependent invariants (M, Jb) of every ORIENTATION CLASS and 1/tau_c of
+// every voxel.  Orientation classes are grains while the texture has not evolved per voxel, voxels after.
+__global__ void __launch_bounds__(kCB) k_prep_orient(Fields f) {
+  const long long o = (long long)blockIdx.x * kCB + threadIdx.x;
+  const long long NO = f.norient, N = f.N;
+  if (o >= NO) return;
+  const long long v = f.orient_rep[o];   // a voxel that carries this orientation (-1: class absent on this rank)
+  if (v < 0) return;
   const PhaseDev &P = c_phase[f.phase[v]];
   double R[9], M[25], Jb[21];
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = f.rot[k * N + v];
   increment_invariants(P, c_cp, R, M, Jb);
 #pragma unroll
-  for (int k = 0; k < 25; ++k) f.mrot[k * N + v] = M[k];
+  for (int k = 0; k < 25; ++k) f.mrot[k * NO + o] = M[k];
 #pragma unroll
-  for (int k = 0; k < 21; ++k) f.jb[k * N + v] = Jb[k];
-  for (int s = 0; s < nsmax; ++s) f.itc[(long long)s * N + v] = 1.0 / f.crss[(long long)s * N + v];
+  for (int k = 0; k < 21; ++k) f.jb[k * NO + o] = Jb[k];
+}
+__global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax) {
+  const long long n = (long long)nsmax * f.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) f.itc[i] = 1.0 / f.crss[i];
 }
 
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
@@ -419,12 +425,14 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
   if (v < N) {
     const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
     const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
+    const long long NO = f.norient;
+    const long long oid = f.orient[v];   // orientation class: grain while the texture is per grain, voxel afterwards
     double sc[6];
     {
       // every load of the voxel is issued before the first use (39+ independent loads in flight)
       double M[25], sig[6], em[6], ep[6], jbv[21];
 #pragma unroll
-      for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * N + v);
+      for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);
 #pragma unroll
       for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
 #pragma unroll
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
 #pragma unroll
       for (int c = 0; c < 6; ++c) ep[c] = __ldg(f.epsp + c * N + v);
 #pragma unroll
-      for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * N + v);
+      for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * NO + oid);
       const int ns = (NS_T > 0) ? NS_T : P.nsys;
       if (NS_T > 0) {
         double tc[NS_T > 0 ? NS_T : 1];
@@ -453,7 +461,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
     nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
     double M[25], sig[6], ds, de;
 #pragma unroll
-    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * N + v);   // second touch: L1/L2 hit
+    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
     constitutive_finish(P, M, sc, jb, so, sig, &ds, &de);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -737,9 +745,18 @@ void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns
   return launch_const_t<0, -2, false, 3>(f, nsmax, partials, st);
 }
 
+__global__ void k_voxel_classes(Fields f) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < f.N; v += (long long)gridDim.x * blockDim.x) {
+    f.orient[v] = (int32_t)v;
+    f.orient_rep[v] = v;
+  }
+}
+void launch_voxel_classes(const Fields &f, cudaStream_t st) { k_voxel_classes<<<592, 256, 0, st>>>(f); }
+
 void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st) {
-  const int nb = (int)((f.N + kCB - 1) / kCB);
-  k_prep_increment<<<nb, kCB, 0, st>>>(f, nsmax);
+  const int nb = (int)((f.norient + kCB - 1) / kCB);
+  k_prep_orient<<<nb, kCB, 0, st>>>(f);
+  k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax);
 }
 
 void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st) {

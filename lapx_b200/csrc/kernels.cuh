@@ -49,6 +49,9 @@ struct Fields {
   double *sig, *e, *epsp, *edotp, *crss, *rot, *gacc, *twinf, *de;
   double *mrot, *jb, *itc;  // per-increment invariants: deviatoric rotation M (25), Jb = S0_c + S_c (21), 1/tau_c
   int32_t *grain, *phase;
+  int32_t *orient;          // orientation class of every voxel (index into mrot/jb tables)
+  long long *orient_rep;    // per class: a local voxel carrying that orientation (or -1)
+  long long norient;        // table length: #grains (texture per grain) or N (texture per voxel)
   long long N;              // local voxels; component stride of every SoA field
 };
 
@@ -74,6 +77,7 @@ void launch_reduce(const double *partials, long long N, double *scratch, double 
 long long partial_doubles(long long N);
 int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
+void launch_voxel_classes(const Fields &f, cudaStream_t st);
 void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st);
 void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st);
 void launch_fill(double *p, long long n, double v, cudaStream_t st);

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -276,6 +277,21 @@ int fetch_report(evp_handle h, evp_iter_report *rep) {
 
 evp_handle g_active = nullptr;  // handle whose tables currently sit in __constant__ memory
 
+// every voxel becomes its own orientation class (after the texture has been changed per voxel)
+int switch_to_voxel_classes(evp_handle h) {
+  const long long N = h->N;
+  if (h->f.norient != N) {
+    cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.orient_rep);
+    h->f.mrot = h->f.jb = nullptr; h->f.orient_rep = nullptr;
+    CUDA_OK(h, cudaMalloc(&h->f.mrot, sizeof(double) * 25 * N));
+    CUDA_OK(h, cudaMalloc(&h->f.jb, sizeof(double) * 21 * N));
+    CUDA_OK(h, cudaMalloc(&h->f.orient_rep, sizeof(long long) * N));
+    h->f.norient = N;
+  }
+  launch_voxel_classes(h->f, h->st);
+  return EVP_OK;
+}
+
 int upload_const(evp_handle h) {
   h->cp.dt = h->dt;
   h->cp.tol_newton = h->ctrl.tol_newton;
@@ -377,8 +393,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   CK(cudaMalloc(&S->f.crss, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.rot, sizeof(double) * 9 * N));
   CK(cudaMalloc(&S->f.gacc, sizeof(double) * N));
-  CK(cudaMalloc(&S->f.mrot, sizeof(double) * 25 * N));
-  CK(cudaMalloc(&S->f.jb, sizeof(double) * 21 * N));
+  CK(cudaMalloc(&S->f.orient, sizeof(int32_t) * N));
   CK(cudaMalloc(&S->f.itc, sizeof(double) * ns * N));
   if (any_twin) CK(cudaMalloc(&S->f.twinf, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.grain, sizeof(int32_t) * N));
@@ -449,7 +464,7 @@ int evp_destroy(evp_handle h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
-  cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc);
+  cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc); cudaFree(h->f.orient); cudaFree(h->f.orient_rep);
   cudaFree(h->f.rot); cudaFree(h->f.gacc); cudaFree(h->f.twinf); cudaFree(h->f.de); cudaFree(h->f.grain); cudaFree(h->f.phase);
   if (h->WB && h->WB != h->WA) cudaFree(h->WB);
   cudaFree(h->WA);
@@ -478,6 +493,45 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   if (phase)
     for (long long v = 0; v < N; ++v)
       if (phase[v] < 0 || phase[v] >= h->nphases) return fail(h, EVP_ERR_ARG, "set_microstructure: phase id out of range");
+  // orientation classes: one per grain if every voxel of a grain carries the same rotation (the usual
+  // starting texture), else one per voxel.  The per-class invariants (M, Jb) are rebuilt every increment.
+  {
+    int32_t gmax = -1;
+    bool ok = true;
+    for (long long v = 0; v < N; ++v) {
+      if (grain[v] < 0) { ok = false; break; }
+      gmax = std::max(gmax, grain[v]);
+    }
+    std::vector<long long> rep;
+    if (ok && getenv("EVP_ORIENT_PER_VOXEL") == nullptr && (long long)gmax + 1 <= N / 4) {
+      rep.assign((size_t)gmax + 1, -1);
+      for (long long v = 0; v < N && ok; ++v) {
+        long long &r = rep[grain[v]];
+        if (r < 0) { r = v; continue; }
+        for (int k = 0; k < 9; ++k)
+          if (rot9[(size_t)k * N + v] != rot9[(size_t)k * N + r]) { ok = false; break; }
+      }
+    } else {
+      ok = false;
+    }
+    std::vector<int32_t> oid;
+    if (!ok) {  // per-voxel classes
+      rep.resize((size_t)N);
+      oid.resize((size_t)N);
+      for (long long v = 0; v < N; ++v) { rep[v] = v; oid[v] = (int32_t)v; }
+    }
+    const long long NO = (long long)rep.size();
+    if (NO != h->f.norient) {
+      cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.orient_rep);
+      h->f.mrot = h->f.jb = nullptr; h->f.orient_rep = nullptr;
+      CUDA_OK(h, cudaMalloc(&h->f.mrot, sizeof(double) * 25 * NO));
+      CUDA_OK(h, cudaMalloc(&h->f.jb, sizeof(double) * 21 * NO));
+      CUDA_OK(h, cudaMalloc(&h->f.orient_rep, sizeof(long long) * NO));
+      h->f.norient = NO;
+    }
+    CUDA_OK(h, cudaMemcpy(h->f.orient_rep, rep.data(), sizeof(long long) * NO, cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemcpy(h->f.orient, ok ? grain : oid.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+  }
   CUDA_OK(h, cudaMemcpyAsync(h->f.grain, grain, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
   if (phase) CUDA_OK(h, cudaMemcpyAsync(h->f.phase, phase, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
   else CUDA_OK(h, cudaMemsetAsync(h->f.phase, 0, sizeof(int32_t) * N, h->st));
@@ -767,6 +821,10 @@ int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
   if (bytes != need) return fail(h, EVP_ERR_ARG, "set_field: size mismatch");
   if (!p) return fail(h, EVP_ERR_STATE, "field is not allocated in this configuration");
   CUDA_OK(h, cudaMemcpyAsync(p, host, need, cudaMemcpyHostToDevice, h->st));
+  if (f == EVP_FIELD_ROTATION) {
+    int rc = switch_to_voxel_classes(h);
+    if (rc) return rc;
+  }
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   return EVP_OK;
 }

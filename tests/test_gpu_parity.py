@@ -22,8 +22,12 @@ def test_backend_is_cuda(product_lib):
     assert s.stream() != 0
 
 
+@pytest.mark.parametrize("per_voxel", [False, True])
 @pytest.mark.parametrize("name", GPU_GOLDEN)
-def test_gpu_matches_numpy_golden(name, product_lib):
+def test_gpu_matches_numpy_golden(name, per_voxel, product_lib, monkeypatch):
+    # orientation classes per grain (default for a per-grain texture) or per voxel (evolved texture)
+    if per_voxel:
+        monkeypatch.setenv("EVP_ORIENT_PER_VOXEL", "1")
     g = load_golden(name)
     s = solver_from_golden(product_lib, product_lib, g)
     s.set_profiling(2)   # keep the strain increment field for the check below
@@ -216,6 +220,35 @@ def test_single_crystal_one_iteration_uniform(product_lib):
     sig = s.get_field(api.FIELD_STRESS)
     assert np.abs(sig - sig.reshape(6, -1)[:, :1].reshape(6, 1, 1, 1)).max() < 1e-9 * np.abs(sig).max()
     assert np.abs(sig[[0, 1, 3, 4, 5]]).max() < 1e-8 * sig[2].mean()
+
+
+def test_rotation_set_field_switches_to_voxel_classes(product_lib, oracle_lib):
+    """evp_set_field(ROTATION) with a per-voxel texture: classes are rebuilt per voxel; parity with the oracle."""
+    rng = np.random.default_rng(8)
+    grid = (16, 16, 16)
+    sols = []
+    rot = None
+    for lib in (product_lib, oracle_lib):
+        s, ids, grot = make_polycrystal(lib, product_lib, grid, 10, seed=4)
+        if rot is None:
+            base = ms.expand_rotations(ids, grot).reshape(9, -1).T.reshape(-1, 3, 3)
+            w = rng.normal(size=(base.shape[0], 3)) * 0.02          # small per-voxel misorientation
+            K = np.zeros((base.shape[0], 3, 3))
+            K[:, 0, 1], K[:, 0, 2], K[:, 1, 2] = -w[:, 2], w[:, 1], -w[:, 0]
+            K -= np.transpose(K, (0, 2, 1))
+            Q, _ = np.linalg.qr(np.eye(3) + K)
+            Q *= np.sign(np.linalg.det(Q))[:, None, None]
+            rot = np.ascontiguousarray(np.einsum("vij,vjk->vik", Q, base).reshape(-1, 9).T).reshape((9,) + ids.shape)
+        s.set_field(api.FIELD_ROTATION, rot)
+        s.set_reference_medium(None)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.uniaxial_tension(1.0))
+        s.begin_increment(2e-4)
+        for _ in range(5):
+            r = s.equilibrium_iter()
+        sols.append((s.get_field(api.FIELD_STRESS), r))
+    assert rel_err(sols[0][0], sols[1][0]) < TOL
+    assert rel_err(sols[0][1].savg[:], sols[1][1].savg[:]) < TOL
 
 
 def test_error_behaviour_matches_oracle(product_lib):
