@@ -178,58 +178,6 @@ EVP_HD bool ldl6_solve(double a[21], double b[6]) {
   return ok;
 }
 
-// Row a4: Newton solve of  Jb*s + dt*edp(s) = g  in the crystal frame (b-basis).
-//   Jb = S0_c + S_c (packed), g = S0:sig_old + e - eps_p (rotated to the crystal frame)
-//   s: in = initial guess (sig_old), out = solution.  ITC(s) returns 1/tau_c of system s.
-// Returns the number of Newton updates; *bad is set when a non-finite value / bad pivot shows up.
-template <class ITC>
-EVP_HD int newton_crystal(const PhaseDev &P, const double Jb[21], const double g[6], double s[6], double dt,
-                          double tol, int itmax, ITC itc, int *bad) {
-  int it = 0;
-  while (it < itmax) {
-    double J[21], F[6];
-#pragma unroll
-    for (int k = 0; k < 21; ++k) J[k] = Jb[k];
-    // F = g - Jb*s - dt*edp   (right-hand side of J*delta = F)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      double acc = g[i];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) acc -= Jb[sidx(i, j)] * s[j];
-      F[i] = acc;
-    }
-    const int ns = P.nsys;
-    for (int q = 0; q < ns; ++q) {
-      double tau = 0.0;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) tau += P.m[q][c] * s[c];
-      double gd, dgd;
-      slip_rate(P, q, tau, itc(q), gd, dgd);
-      const double a = dt * gd, bcoef = dt * dgd;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) F[c] -= a * P.m[q][c];
-#pragma unroll
-      for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = i; j < 5; ++j) J[sidx(i, j)] += bcoef * P.mm[q][s5idx(i, j)];
-    }
-    const bool ok = ldl6_solve(J, F);
-    double dn = 0.0, sn = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      s[i] += F[i];
-      dn += F[i] * F[i];
-      sn += s[i] * s[i];
-    }
-    ++it;
-    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
-    if (dn <= tol * tol * sn) break;
-  }
-  return it;
-}
-
-
-
 // x^K with a compile-time exponent (square-and-multiply, K = n-1 of the power law)
 template <int K>
 EVP_HD double pow_ct(double x) {
@@ -252,7 +200,7 @@ EVP_HD void slip_rate_t(const PhaseDev &P, int s, double tau, double itc, double
   dgd = g * P.nrate[s] * itc;
 }
 
-// Row a4, production form.  NS_T > 0: the loop over systems is fully unrolled (tables become
+// Row a4: Newton solve of  Jb*s + dt*edp(s) = g  in the crystal frame (b-basis).  NS_T > 0: the loop over systems is fully unrolled (tables become
 // constant-bank operands);  NS_T == 0: runtime P.nsys.  JB(k)/GV(i): accessors of the packed
 // Jb = S0_c + S_c and of g (kept in shared memory by the kernel, in arrays by the emulation).
 template <int NS_T, int NPOW_T, class JB, class GV, class ITC>
@@ -340,85 +288,7 @@ EVP_HD void rotate_s0(const double *S0b, const double M[25], double out[21]) {
   }
 }
 
-// Rows a4+a5+a6 for one voxel.  sig: in = sigma_old (Cartesian 6), out = sigma_new.
-// em = e - eps_p (Cartesian 6).  ITC: accessor of 1/tau_c per system.
-// Outputs: *ds = |sig_new - sig_old|, *de = |S0:(sig_new - sig_old)|, returns Newton iterations.
-template <class ITC>
-EVP_HD int constitutive_voxel(const PhaseDev &P, const ConstParams &cp, const double R[9], double sig[6], const double em[6],
-                              ITC itc, double *ds, double *de, int *bad) {
-  double M[25];
-  rot_b5(R, M);
-  double so[6], eb[6];
-  cart_to_b(sig, so);
-  cart_to_b(em, eb);
-  // g = S0:sig_old + e - eps_p   (sample frame)
-  double g[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double acc = eb[i];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) acc += cp.S0b[sidx(i, j)] * so[j];
-    g[i] = acc;
-  }
-  // to the crystal frame: a_c = M^T a_s on the deviatoric part
-  double gc[6], sc[6], s0c[6];
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-    double x = 0.0, y = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {
-      x += M[b * 5 + a] * g[b];
-      y += M[b * 5 + a] * so[b];
-    }
-    gc[a] = x;
-    sc[a] = y;
-  }
-  gc[5] = g[5];
-  sc[5] = so[5];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) s0c[a] = sc[a];
-  double Jb[21];
-  if (cp.iso_c0) {
-#pragma unroll
-    for (int k = 0; k < 21; ++k) Jb[k] = cp.S0b[k];
-  } else {
-    rotate_s0(cp.S0b, M, Jb);
-  }
-#pragma unroll
-  for (int k = 0; k < 21; ++k) Jb[k] += P.Sc[k];
-  const int nit = newton_crystal(P, Jb, gc, sc, cp.dt, cp.tol_newton, cp.newton_itmax, itc, bad);
-  // norms (row a6): |dsig| and |S0:dsig| = |(Jb - Sc) dsig|, both rotation invariant
-  double d[6], ds2 = 0.0, de2 = 0.0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a) {
-    d[a] = sc[a] - s0c[a];
-    ds2 += d[a] * d[a];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) acc += (Jb[sidx(i, j)] - P.Sc[sidx(i, j)]) * d[j];
-    de2 += acc * acc;
-  }
-  *ds = sqrt(ds2);
-  *de = sqrt(de2);
-  // back to the sample frame; row a5: lambda_new == sigma_new, one stored field
-  double sb[6];
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-    double x = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) x += M[a * 5 + b] * sc[b];
-    sb[a] = x;
-  }
-  sb[5] = sc[5];
-  b_to_cart(sb, sig);
-  return nit;
-}
-
-
-// Production split of constitutive_voxel.
+// Rows a4+a5+a6 for one voxel, split in three stages.
 //  increment_invariants : per voxel, once per increment — the deviatoric rotation M (25) and the
 //                         packed Jb = S0_c + S_c (21); both depend only on the lattice orientation,
 //                         which is constant within an increment.
@@ -436,9 +306,8 @@ EVP_HD void increment_invariants(const PhaseDev &P, const ConstParams &cp, const
   }
 }
 
-template <class STG, class STS>
-EVP_HD void constitutive_prep(const ConstParams &cp, const double M[25], const double sig[6], const double em[6], STG stG, STS stS,
-                              double sc[6]) {
+template <class MV, class STG, class STS>
+EVP_HD void constitutive_prep(const ConstParams &cp, MV M, const double sig[6], const double em[6], STG stG, STS stS, double sc[6]) {
   double so[6], eb[6];
   cart_to_b(sig, so);
   cart_to_b(em, eb);
@@ -455,8 +324,9 @@ EVP_HD void constitutive_prep(const ConstParams &cp, const double M[25], const d
     double x = 0.0, y = 0.0;
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
-      x += M[b * 5 + a] * g[b];
-      y += M[b * 5 + a] * so[b];
+      const double m = M(b * 5 + a);
+      x += m * g[b];
+      y += m * so[b];
     }
     stG(a, x);
     sc[a] = y;
@@ -467,9 +337,8 @@ EVP_HD void constitutive_prep(const ConstParams &cp, const double M[25], const d
   for (int a = 0; a < 6; ++a) stS(a, sc[a]);
 }
 
-template <class JB, class SV>
-EVP_HD void constitutive_finish(const PhaseDev &P, const double M[25], const double sc[6], JB Jb, SV sold, double sig[6], double *ds,
-                                double *de) {
+template <class MV, class JB, class SV>
+EVP_HD void constitutive_finish(const PhaseDev &P, MV M, const double sc[6], JB Jb, SV sold, double sig[6], double *ds, double *de) {
   double d[6], ds2 = 0.0, de2 = 0.0, acc[6];
 #pragma unroll
   for (int a = 0; a < 6; ++a) {
@@ -494,7 +363,7 @@ EVP_HD void constitutive_finish(const PhaseDev &P, const double M[25], const dou
   for (int a = 0; a < 5; ++a) {
     double x = 0.0;
 #pragma unroll
-    for (int b = 0; b < 5; ++b) x += M[a * 5 + b] * sc[b];
+    for (int b = 0; b < 5; ++b) x += M(a * 5 + b) * sc[b];
     sb[a] = x;
   }
   sb[5] = sc[5];

@@ -383,6 +383,10 @@ __device__ __forceinline__ void warp_partials_store(const double vals[NV], int v
   if (lane == 0) partials[(long long)NV * nw + gw] = (double)m;
 }
 
+struct RegAcc25 {   // register-resident 5x5 rotation (indices are compile-time constants after unrolling)
+  const double *m;
+  __device__ __forceinline__ double operator()(int k) const { return m[k]; }
+};
 struct SmAcc {      // strided per-thread array in shared memory: element k of this thread
   double *p;
   __device__ __forceinline__ double operator()(int k) const { return p[k * kCB]; }
@@ -415,13 +419,28 @@ __global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax) {
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
 // (tables addressed as c_phase[0], i.e. immediate constant-bank operands).
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
-__global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *__restrict__ partials, long long nw) {
+__global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *__restrict__ partials, long long nw, int pf_dist) {
   extern __shared__ double smd[];  // [21 Jb | 6 g | 6 s_old | nsmax 1/tau_c] x kCB
   const int tid = threadIdx.x;
   const long long v = (long long)blockIdx.x * kCB + tid;
   const long long N = f.N;
   double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
   int nit = 0;
+  // L2 prefetch of the per-voxel streams of the block that runs one residency wave later: with ~12 warps per SM
+  // the loads below would otherwise expose DRAM latency (ncu: long-scoreboard stalls on their first use)
+  {
+    const long long vp = ((long long)blockIdx.x + pf_dist) * kCB;
+    if (vp + kCB <= N) {
+      const int nstream = 18 + ((NS_T > 0) ? NS_T : 0);
+      if (tid < nstream) {
+        const double *base = (tid < 6) ? f.sig + (long long)tid * N : (tid < 12) ? f.e + (long long)(tid - 6) * N
+                             : (tid < 18) ? f.epsp + (long long)(tid - 12) * N : f.itc + (long long)(tid - 18) * N;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + vp), "r"(kCB * 8) : "memory");
+      } else if (tid == nstream) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f.orient + vp), "r"(kCB * 4) : "memory");
+      }
+    }
+  }
   if (v < N) {
     const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
     const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
@@ -455,14 +474,14 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
       for (int k = 0; k < 21; ++k) jb(k, jbv[k]);
 #pragma unroll
       for (int c = 0; c < 6; ++c) em[c] -= ep[c];
-      constitutive_prep(c_cp, M, sig, em, gv, so, sc);
+      constitutive_prep(c_cp, RegAcc25{M}, sig, em, gv, so, sc);
     }
     int bad = 0;
     nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
     double M[25], sig[6], ds, de;
 #pragma unroll
     for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
-    constitutive_finish(P, M, sc, jb, so, sig, &ds, &de);
+    constitutive_finish(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       f.sig[c * N + v] = sig[c];
@@ -727,7 +746,9 @@ static void launch_const_t(const Fields &f, int nsmax, double *partials, cudaStr
     cudaFuncSetAttribute(k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
-  k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, partials, num_warps(f.N));
+  static int pf = -1;
+  if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * MINB;   // prefetch distance in blocks (0 = off)
+  k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, partials, num_warps(f.N), pf > 0 ? pf : (1 << 30));
 }
 
 // variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase

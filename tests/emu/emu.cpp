@@ -53,9 +53,9 @@ int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig
           int *bad) {
   double M[25], jb[21], g[6], so[6], sc[6];
   increment_invariants(P, cp, R, M, jb);                       // k_prep_increment
-  constitutive_prep(cp, M, sig, em, ArrAcc{g}, ArrAcc{so}, sc);  // k_constitutive_t
+  constitutive_prep(cp, ArrAcc{M}, sig, em, ArrAcc{g}, ArrAcc{so}, sc);  // k_constitutive_t
   const int nit = newton_crystal_t<NS_T, NPOW_T>(P, ArrAcc{jb}, ArrAcc{g}, sc, cp.dt, cp.tol_newton, cp.newton_itmax, ArrAcc{itc}, bad);
-  constitutive_finish(P, M, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
+  constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
 }  // namespace
@@ -76,7 +76,7 @@ int emu_fft(int n, int inv, int nlines, double *data) {
 #undef E_
 }
 
-// one voxel of k_constitutive.  c0_voigt: reference medium.  Returns Newton iterations.
+// one voxel of the generic kernel variant; force_aniso exercises the rotated-S0 path on an isotropic medium
 int emu_constitutive(const evp_phase *ph, const double *c0_voigt, const double *R, double *sig, const double *e, const double *epsp,
                      const double *crss, double dt, double tol, int itmax, double *ds, double *de, int *bad, int force_aniso) {
   PhaseDev P;
@@ -92,7 +92,7 @@ int emu_constitutive(const evp_phase *ph, const double *c0_voigt, const double *
   for (int s = 0; s < ph->nsys; ++s) itc[s] = 1.0 / crss[s];
   for (int c = 0; c < 6; ++c) em[c] = e[c] - epsp[c];
   *bad = 0;
-  return constitutive_voxel(P, cp, R, sig, em, ItcArr{itc}, ds, de, bad);
+  return run_t<0, -2>(P, cp, R, sig, em, itc, ds, de, bad);
 }
 
 // Green operator at one frequency (k_zfused inner stage).  lam/out: 6 complex (re,im interleaved)
