@@ -282,25 +282,15 @@ def main():
     hbm, peak_src = peaks()
     local_grid = (grid[0], grid[1], grid[2] // world)
     ab = algorithmic_bytes(local_grid, nsys)
-    fused = kms[4] < 1e-3 and kms[0] < 0.05 * kms[5]     # x passes live inside the fused row kernel
-    names = list(KNAMES)
-    if fused:
-        nl = local_grid[0] * local_grid[1] * local_grid[2]
-        ncl = (local_grid[0] // 2 + 1) * local_grid[1] * local_grid[2]
-        # row kernel: spectra in + out, e read+write, sigma read+write, eps_p, 1/tau_c, orientation class id
-        ab["constitutive"] = 192 * ncl + (5 * 48 + 8 * nsys + 4) * nl
-        names[5] = "row_fused(x_inv+update+newton+x_fwd)"
     kern = []
     for i, k in enumerate(KNAMES):
-        if fused and i in (0, 4):
-            continue
         gbs = ab[k] / (kms[i] * 1e-3) / 1e9 if kms[i] > 0 else 0.0
-        kern.append({"name": names[i], "ms": round(float(kms[i]), 4), "algorithmic_bytes": int(ab[k]), "gbs": round(gbs, 1),
+        kern.append({"name": k, "ms": round(float(kms[i]), 4), "algorithmic_bytes": int(ab[k]), "gbs": round(gbs, 1),
                      "frac_hbm": round(gbs / hbm, 4)})
-    dom = max(range(len(kern)), key=lambda i: kern[i]["ms"])
-    roof = {"kernel": kern[dom]["name"], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s",
+    dom = max(range(6), key=lambda i: kms[i])
+    roof = {"kernel": KNAMES[dom], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s",
             "frac": kern[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
-            "note": "the constitutive / row kernel is fp64-pipe bound (DESIGN.md §4); its HBM fraction is reported for uniformity"}
+            "note": "constitutive is fp64-pipe bound (DESIGN.md §4); its HBM fraction is reported for uniformity"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,7 +305,7 @@ def main():
         "e2e": {"value": N * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 42 * 8, "d2h_bytes_per_step": 616,
                 "what": "evp_set_loading + evp_equilibrium_iter per step through the C ABI: BC upload, report download, host sync; "
                         "fields stay device resident by design (one-off transfer cost under config.setup)"},
-        "gpu_launches": (7 if fused else 9) * args.steps,
+        "gpu_launches": 9 * args.steps,
         "clocks": clk,
     }
     if not args.no_cpu_baseline:

@@ -71,35 +71,30 @@ struct OffES {
 };
 
 template <int N, int R, int NS, bool INV, class OFF>
-__device__ __forceinline__ void fft_pass(double2 *s, int q, OFF off, TwLdg tw, bool active) {
+__device__ __forceinline__ void fft_pass(double2 *s, int q, OFF off, TwLdg tw) {
   double2 v[8];
-  if (active) pass_load<N, R>(s, q, v, off);
+  pass_load<N, R>(s, q, v, off);
   __syncthreads();
-  if (active) pass_store<N, R, NS, INV>(s, q, v, off, tw);
+  pass_store<N, R, NS, INV>(s, q, v, off, tw);
   __syncthreads();
 }
 
 template <int N, int NS, bool INV, class OFF>
-__device__ __forceinline__ void fft_rest(double2 *s, int q, OFF off, TwLdg tw, bool active) {
+__device__ __forceinline__ void fft_rest(double2 *s, int q, OFF off, TwLdg tw) {
   if constexpr (NS < N) {
-    fft_pass<N, 8, NS, INV>(s, q, off, tw, active);
-    fft_rest<N, NS * 8, INV>(s, q, off, tw, active);
+    fft_pass<N, 8, NS, INV>(s, q, off, tw);
+    fft_rest<N, NS * 8, INV>(s, q, off, tw);
   }
 }
 
 // all threads of the block must call this (contains __syncthreads); threads with active == false
 // only take part in the barriers.
 template <int N, bool INV, class OFF>
-__device__ __forceinline__ void block_fft(double2 *s, int q, OFF off, TwLdg tw, bool active = true) {
+__device__ __forceinline__ void block_fft(double2 *s, int q, OFF off, TwLdg tw) {
   constexpr int R0 = first_radix(N);
-  fft_pass<N, R0, 1, INV>(s, q, off, tw, active);
-  fft_rest<N, R0, INV>(s, q, off, tw, active);
+  fft_pass<N, R0, 1, INV>(s, q, off, tw);
+  fft_rest<N, R0, INV>(s, q, off, tw);
 }
-// line padded by one element per eight: conflict-free radix-8 scatter when one warp works on one line
-struct OffPad {
-  int base;
-  __device__ __forceinline__ int operator()(int i) const { return base + i + (i >> 3); }
-};
 
 // ---------------------------------------------------------------------------------------------
 // K2: x forward.  Block = XL rows of one component pair.
@@ -423,78 +418,6 @@ __global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax) {
 
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
 // (tables addressed as c_phase[0], i.e. immediate constant-bank operands).
-// one voxel of rows a4+a5+a6.  e_in: compatible strain of the voxel; smd: the block's K1 scratch.
-// Adds the norm contributions to vals[0..9] and returns the Newton iteration count.
-template <int NS_T, int NPOW_T, bool ONEPH>
-__device__ __forceinline__ int voxel_update(const Fields &f, long long v, int tid, double *smd, const double e_in[6], double sig[6],
-                                            double vals[10]) {
-  const long long N = f.N;
-  const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
-  const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
-  const long long NO = f.norient;
-  const long long oid = f.orient[v];   // orientation class: grain while the texture is per grain, voxel afterwards
-  double sc[6];
-  {
-    // every load of the voxel is issued before the first use
-    double M[25], em[6], ep[6], jbv[21];
-#pragma unroll
-    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) ep[c] = __ldg(f.epsp + c * N + v);
-#pragma unroll
-    for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * NO + oid);
-    const int ns = (NS_T > 0) ? NS_T : P.nsys;
-    if (NS_T > 0) {
-      double tc[NS_T > 0 ? NS_T : 1];
-#pragma unroll
-      for (int s = 0; s < NS_T; ++s) tc[s] = __ldg(f.itc + (long long)s * N + v);
-#pragma unroll
-      for (int s = 0; s < NS_T; ++s) itc(s, tc[s]);
-    } else {
-      for (int s = 0; s < ns; ++s) itc(s, __ldg(f.itc + (long long)s * N + v));
-    }
-#pragma unroll
-    for (int k = 0; k < 21; ++k) jb(k, jbv[k]);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) em[c] = e_in[c] - ep[c];
-    constitutive_prep(c_cp, RegAcc25{M}, sig, em, gv, so, sc);
-  }
-  int bad = 0;
-  const int nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
-  double M[25], ds, de;
-#pragma unroll
-  for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
-  constitutive_finish(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    f.sig[c * N + v] = sig[c];
-    vals[2 + c] += sig[c];
-  }
-  vals[0] += ds;
-  vals[1] += de;
-  vals[8] += (double)nit;
-  vals[9] += (double)bad;
-  return nit;
-}
-
-// L2 prefetch (cp.async.bulk.prefetch) of `count` voxels of the per-voxel streams starting at voxel vp:
-// with ~12 warps per SM the first-use loads would otherwise expose DRAM latency (ncu: long scoreboard)
-template <int NS_T>
-__device__ __forceinline__ void prefetch_streams(const Fields &f, long long vp, int count, int tid) {
-  const long long N = f.N;
-  if (vp + count > N) return;
-  const int nstream = 18 + ((NS_T > 0) ? NS_T : 0);
-  if (tid < nstream) {
-    const double *base = (tid < 6) ? f.sig + (long long)tid * N : (tid < 12) ? f.e + (long long)(tid - 6) * N
-                         : (tid < 18) ? f.epsp + (long long)(tid - 12) * N : f.itc + (long long)(tid - 18) * N;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + vp), "r"(count * 8) : "memory");
-  } else if (tid == nstream) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f.orient + vp), "r"(count * 4) : "memory");
-  }
-}
-
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
 __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *__restrict__ partials, long long nw, int pf_dist) {
   extern __shared__ double smd[];  // [21 Jb | 6 g | 6 s_old | nsmax 1/tau_c] x kCB
@@ -503,108 +426,73 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
   const long long N = f.N;
   double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
   int nit = 0;
-  prefetch_streams<NS_T>(f, ((long long)blockIdx.x + pf_dist) * kCB, kCB, tid);   // block one residency wave later
+  // L2 prefetch of the per-voxel streams of the block that runs one residency wave later: with ~12 warps per SM
+  // the loads below would otherwise expose DRAM latency (ncu: long-scoreboard stalls on their first use)
+  {
+    const long long vp = ((long long)blockIdx.x + pf_dist) * kCB;
+    if (vp + kCB <= N) {
+      const int nstream = 18 + ((NS_T > 0) ? NS_T : 0);
+      if (tid < nstream) {
+        const double *base = (tid < 6) ? f.sig + (long long)tid * N : (tid < 12) ? f.e + (long long)(tid - 6) * N
+                             : (tid < 18) ? f.epsp + (long long)(tid - 12) * N : f.itc + (long long)(tid - 18) * N;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + vp), "r"(kCB * 8) : "memory");
+      } else if (tid == nstream) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f.orient + vp), "r"(kCB * 4) : "memory");
+      }
+    }
+  }
   if (v < N) {
-    double e[6], sig[6];
+    const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
+    const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
+    const long long NO = f.norient;
+    const long long oid = f.orient[v];   // orientation class: grain while the texture is per grain, voxel afterwards
+    double sc[6];
+    {
+      // every load of the voxel is issued before the first use (39+ independent loads in flight)
+      double M[25], sig[6], em[6], ep[6], jbv[21];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) e[c] = f.e[c * N + v];
-    nit = voxel_update<NS_T, NPOW_T, ONEPH>(f, v, tid, smd, e, sig, vals);
+      for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sig[c] = f.sig[c * N + v];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) em[c] = f.e[c * N + v];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) ep[c] = __ldg(f.epsp + c * N + v);
+#pragma unroll
+      for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * NO + oid);
+      const int ns = (NS_T > 0) ? NS_T : P.nsys;
+      if (NS_T > 0) {
+        double tc[NS_T > 0 ? NS_T : 1];
+#pragma unroll
+        for (int s = 0; s < NS_T; ++s) tc[s] = __ldg(f.itc + (long long)s * N + v);
+#pragma unroll
+        for (int s = 0; s < NS_T; ++s) itc(s, tc[s]);
+      } else {
+        for (int s = 0; s < ns; ++s) itc(s, __ldg(f.itc + (long long)s * N + v));
+      }
+#pragma unroll
+      for (int k = 0; k < 21; ++k) jb(k, jbv[k]);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) em[c] -= ep[c];
+      constitutive_prep(c_cp, RegAcc25{M}, sig, em, gv, so, sc);
+    }
+    int bad = 0;
+    nit = newton_crystal_t<NS_T, NPOW_T>(P, jb, gv, sc, c_cp.dt, c_cp.tol_newton, c_cp.newton_itmax, itc, &bad);
+    double M[25], sig[6], ds, de;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
+    constitutive_finish(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      f.sig[c * N + v] = sig[c];
+      vals[2 + c] = sig[c];
+    }
+    vals[0] = ds;
+    vals[1] = de;
+    vals[8] = (double)nit;
+    vals[9] = (double)bad;
   }
   warp_partials_store<10>(vals, nit, partials, nw);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused row kernel (rows a3 + a4..a6 + a1 of the next iteration): one block owns one x-line of NX voxels.
-//   x inverse FFT of the 6 strain-correction spectra -> e <- e - de + dE -> Newton per voxel ->
-//   x forward FFT of the new stress -> 6 half spectra.  e and sigma make one HBM round trip less each
-//   and the memory traffic of both x passes hides under the fp64 work of the Newton solve.
-// ---------------------------------------------------------------------------------------------
-template <int NX>
-struct RowCfg {
-  static constexpr int TPL = NX / 8;                       // FFT threads per line
-  static constexpr int LPR = (kCB / TPL > 0) ? kCB / TPL : 1;  // lines per round
-  static constexpr int LSP = NX + NX / 8 + 1;              // padded line length (elements)
-  static constexpr int VPT = NX / kCB;                     // voxels per thread
-  static constexpr size_t zbytes = (size_t)3 * LSP * sizeof(double2);
-};
-
-template <int NX, int NS_T, int NPOW_T, bool ONEPH>
-__global__ void __launch_bounds__(kCB, 3) k_row_fused(double2 *__restrict__ W, SpecLayout Lay, Fields f, const MacroDev *__restrict__ macro,
-                                                      double *__restrict__ partials, long long nw, int pf_dist,
-                                                      const double2 *__restrict__ twp) {
-  using C = RowCfg<NX>;
-  static_assert(NX >= kCB && C::TPL <= kCB, "fused row kernel needs 128 <= NX <= 1024");
-  extern __shared__ __align__(16) double smraw[];
-  double2 *Z = reinterpret_cast<double2 *>(smraw);                  // 3 padded complex lines
-  double *smd = smraw + C::zbytes / sizeof(double);                 // K1 scratch
-  const int tid = threadIdx.x;
-  const int row = blockIdx.x;                                       // (zl, y) line of the local slab
-  const long long N = f.N;
-  const int ny = Lay.nyl;
-  const int zl = row >> Lay.lg_nyl, y = row & (ny - 1);
-  constexpr int nxh = NX / 2 + 1;
-  prefetch_streams<NS_T>(f, ((long long)row + pf_dist) * NX, NX, tid);
-  // --- x inverse: Z_p(k) = A_2p(k) + i A_2p+1(k), Hermitian completion for k > NX/2
-  for (int idx = tid; idx < 3 * nxh; idx += kCB) {
-    const int p = idx / nxh, k = idx - p * nxh;
-    const long long o = Lay.row_ysplit(2 * p, zl, y) + k;
-    double2 A = W[o], B = W[o + Lay.cstride];
-    if (k == 0 || k == NX / 2) { A.y = 0.0; B.y = 0.0; }
-    double2 *zp = Z + p * C::LSP;
-    zp[k + (k >> 3)] = make_double2(A.x - B.y, A.y + B.x);
-    if (k > 0 && k < NX / 2) {
-      const int km = NX - k;
-      zp[km + (km >> 3)] = make_double2(A.x + B.y, B.x - A.y);
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int l0 = 0; l0 < 3; l0 += C::LPR) {
-    const int l = l0 + tid / C::TPL;
-    block_fft<NX, true>(Z, tid % C::TPL, OffPad{l * C::LSP}, TwLdg{twp}, l < 3 && tid / C::TPL < C::LPR);
-  }
-  // --- per voxel: strain update, Newton, new stress back into the lines
-  double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  int nitmax = 0;
-  double dE[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) dE[c] = macro->dEpend[c];
-#pragma unroll 1
-  for (int j = 0; j < C::VPT; ++j) {
-    const int x = tid + j * kCB;
-    const long long v = (long long)row * NX + x;
-    const int xo = x + (x >> 3);
-    double e[6], sig[6];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const double2 d = Z[p * C::LSP + xo];
-      e[2 * p] = f.e[(long long)(2 * p) * N + v] + dE[2 * p] - d.x;
-      e[2 * p + 1] = f.e[(long long)(2 * p + 1) * N + v] + dE[2 * p + 1] - d.y;
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) f.e[c * N + v] = e[c];
-    const int nit = voxel_update<NS_T, NPOW_T, ONEPH>(f, v, tid, smd, e, sig, vals);
-    nitmax = max(nitmax, nit);
-#pragma unroll
-    for (int p = 0; p < 3; ++p) Z[p * C::LSP + xo] = make_double2(sig[2 * p], sig[2 * p + 1]);
-  }
-  __syncthreads();
-  // --- x forward of the new stress (row a1 of the next iteration)
-#pragma unroll 1
-  for (int l0 = 0; l0 < 3; l0 += C::LPR) {
-    const int l = l0 + tid / C::TPL;
-    block_fft<NX, false>(Z, tid % C::TPL, OffPad{l * C::LSP}, TwLdg{twp}, l < 3 && tid / C::TPL < C::LPR);
-  }
-  for (int idx = tid; idx < 3 * nxh; idx += kCB) {
-    const int p = idx / nxh, k = idx - p * nxh;
-    const double2 *zp = Z + p * C::LSP;
-    const int km = (NX - k) & (NX - 1);
-    const double2 zk = zp[k + (k >> 3)], zm = zp[km + (km >> 3)];
-    const long long o = Lay.row_ysplit(2 * p, zl, y) + k;
-    W[o] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-    W[o + Lay.cstride] = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
-  }
-  warp_partials_store<10>(vals, nitmax, partials, nw);
 }
 
 // second stage of the reductions: fixed-order two-level sum of the warp partials (deterministic)
@@ -878,47 +766,6 @@ void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns
   return launch_const_t<0, -2, false, 3>(f, nsmax, partials, st);
 }
 
-template <int NX, int NS_T, int NPOW_T, bool ONEPH>
-static void launch_row_t(double2 *W, const SpecLayout &L, const Fields &f, int nsmax, const MacroDev *macro, double *partials, int nrows,
-                         const double2 *tw, cudaStream_t st) {
-  using C = RowCfg<NX>;
-  const size_t smem = C::zbytes + (size_t)(33 + (nsmax > 0 ? nsmax : 1)) * kCB * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_row_fused<NX, NS_T, NPOW_T, ONEPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024);
-    cudaFuncSetAttribute(k_row_fused<NX, NS_T, NPOW_T, ONEPH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_done = true;
-  }
-  static int pf = -1;
-  if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * 3;
-  k_row_fused<NX, NS_T, NPOW_T, ONEPH><<<nrows, kCB, smem, st>>>(W, L, f, macro, partials, (long long)nrows * (kCB / 32), pf > 0 ? pf : (1 << 30), tw);
-}
-
-bool row_fused_supported(int nx) { return nx == 128 || nx == 256 || nx == 512; }
-long long row_partial_doubles(int nrows) { return 11LL * nrows * (kCB / 32); }
-
-template <int NX>
-static void launch_row_nx(double2 *W, const SpecLayout &L, const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow,
-                          const MacroDev *macro, double *partials, int nrows, const double2 *tw, cudaStream_t st) {
-  const bool one = nphases == 1;
-  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_row_t<NX, 12, 9, true>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_row_t<NX, 12, 19, true>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-  if (one && uniform_ns == 12) return launch_row_t<NX, 12, -2, true>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-  if (one && uniform_ns == 24 && uniform_npow == 9) return launch_row_t<NX, 24, 9, true>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-  if (one && uniform_ns == 24) return launch_row_t<NX, 24, -2, true>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-  return launch_row_t<NX, 0, -2, false>(W, L, f, nsmax, macro, partials, nrows, tw, st);
-}
-
-// x inverse + strain update + constitutive + x forward in one kernel; partial layout: 4 warps per row
-void launch_row_fused(int nx, double2 *W, const SpecLayout &L, const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow,
-                      const MacroDev *macro, double *partials, int nrows, const double2 *tw, cudaStream_t st) {
-  if (nx == 128) launch_row_nx<128>(W, L, f, nsmax, nphases, uniform_ns, uniform_npow, macro, partials, nrows, tw, st);
-  else if (nx == 256) launch_row_nx<256>(W, L, f, nsmax, nphases, uniform_ns, uniform_npow, macro, partials, nrows, tw, st);
-  else if (nx == 512) launch_row_nx<512>(W, L, f, nsmax, nphases, uniform_ns, uniform_npow, macro, partials, nrows, tw, st);
-}
-
-void launch_reduce_warps(const double *partials, long long nw, double *scratch, double *totals, cudaStream_t st);
-
 __global__ void k_voxel_classes(Fields f) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < f.N; v += (long long)gridDim.x * blockDim.x) {
     f.orient[v] = (int32_t)v;
@@ -939,13 +786,11 @@ void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cuda
   k_commit<<<nb, kCB, smem, st>>>(f, dt, partials, num_warps(f.N));
 }
 
-void launch_reduce_warps(const double *partials, long long nw, double *scratch, double *totals, cudaStream_t st) {
+void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) {
+  const long long nw = num_warps(N);
   const int nb = (int)((nw < kRedBlocks) ? nw : kRedBlocks);
   k_reduce1<<<nb, 256, 0, st>>>(partials, nw, scratch);
   k_reduce2<<<1, 32, 0, st>>>(scratch, nb, totals);
-}
-void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) {
-  launch_reduce_warps(partials, num_warps(N), scratch, totals, st);
 }
 void launch_macro(const double *totals, MacroDev *macro, double ntot, cudaStream_t st) { k_macro<<<1, 32, 0, st>>>(totals, macro, ntot); }
 void launch_fill(double *p, long long n, double v, cudaStream_t st) { k_fill<<<592, 256, 0, st>>>(p, n, v); }

@@ -75,11 +75,6 @@ void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const Macr
 void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st);
 void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st);
 long long partial_doubles(long long N);
-bool row_fused_supported(int nx);
-long long row_partial_doubles(int nrows);
-void launch_row_fused(int nx, double2 *W, const SpecLayout &L, const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow,
-                      const MacroDev *macro, double *partials, int nrows, const double2 *tw, cudaStream_t st);
-void launch_reduce_warps(const double *partials, long long nw, double *scratch, double *totals, cudaStream_t st);
 int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
 void launch_voxel_classes(const Fields &f, cudaStream_t st);

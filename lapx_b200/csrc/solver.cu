@@ -95,8 +95,6 @@ struct evp_solver {
   ConstParams cp{};
   GreenConst green{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
-  bool spec_ready = false;   // WB holds the x-transformed spectra of the current stress (left there by the fused row kernel)
-  bool allow_fused = true;
   evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100};
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};
@@ -250,53 +248,6 @@ int enqueue_constitutive(evp_handle h) {
   launch_macro(h->d_totals, h->d_macro, h->Ntot, h->st);
   rec(h, 8);
   return EVP_OK;
-}
-
-bool use_fused(evp_handle h) { return h->allow_fused && row_fused_supported(h->nx) && !(h->flags & 2); }
-
-// one whole iteration with the fused row kernel:  [x fwd only if the spectra are stale] -> y fwd -> (a2a) ->
-// z fused -> (a2a) -> y inv -> row kernel {x inv, e update, Newton, x fwd of the new stress} -> reductions -> macro
-int enqueue_iteration_fused(evp_handle h) {
-  const int nrows = h->ny * h->nzl;
-  rec(h, 0);
-  if (!h->spec_ready) launch_xfwd(h->nx, h->f.sig, h->WB, h->N, nrows, h->Lplain, h->twx, h->st);
-  rec(h, 1);
-  launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_split, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzl, h->twy, h->st);
-  rec(h, 2);
-  if (h->nranks > 1) {
-    int rc = all_to_all(h, h->WA, h->WB);
-    if (rc) return rc;
-  }
-  rec(h, 3);
-  launch_zfused(h->nz, false, h->tm_z, h->ti_z, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
-  rec(h, 4);
-  if (h->nranks > 1) {
-    int rc = all_to_all(h, h->WB, h->WA);
-    if (rc) return rc;
-  }
-  rec(h, 5);
-  launch_ypass(h->ny, true, h->tm_y_split, h->tm_y_plain, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  rec(h, 6);
-  rec(h, 7);
-  launch_row_fused(h->nx, h->WB, h->Lplain, h->f, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->d_macro, h->d_partials, nrows,
-                   h->twx, h->st);
-  launch_reduce_warps(h->d_partials, (long long)nrows * 4, h->d_scratch, h->d_totals, h->st);
-  if (h->nranks > 1) {
-    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, h->comm, h->st);
-    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, h->comm, h->st);
-    if (rc) return nccl_check(h, rc, "nccl allreduce");
-  }
-  launch_macro(h->d_totals, h->d_macro, h->Ntot, h->st);
-  rec(h, 8);
-  h->spec_ready = true;
-  return EVP_OK;
-}
-
-int enqueue_iteration(evp_handle h) {
-  if (use_fused(h)) return enqueue_iteration_fused(h);
-  int rc = enqueue_green(h);
-  if (rc == 0) rc = enqueue_constitutive(h);
-  return rc;
 }
 
 int fetch_report(evp_handle h, evp_iter_report *rep) {
@@ -603,8 +554,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   }
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   CUDA_OK(h, cudaGetLastError());
-  h->have_micro = true; h->in_incr = false; h->spec_ready = false;
-  h->allow_fused = getenv("EVP_NO_FUSE") == nullptr;
+  h->have_micro = true; h->in_incr = false;
   return EVP_OK;
 }
 
@@ -751,7 +701,6 @@ int evp_begin_increment(evp_handle h, double dt) {
 int evp_op_green(evp_handle h) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_green outside an increment");
   activate(h);
-  h->spec_ready = false;   // the unfused path overwrites the work buffer
   int rc = enqueue_green(h);
   if (rc) return rc;
   CUDA_OK(h, cudaStreamSynchronize(h->st));
@@ -762,7 +711,6 @@ int evp_op_green(evp_handle h) {
 int evp_op_constitutive(evp_handle h, evp_iter_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_constitutive outside an increment");
   activate(h);
-  h->spec_ready = false;
   int rc = enqueue_constitutive(h);
   if (rc) return rc;
   rc = fetch_report(h, rep);
@@ -773,7 +721,8 @@ int evp_op_constitutive(evp_handle h, evp_iter_report *rep) {
 int evp_equilibrium_iter(evp_handle h, evp_iter_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iter outside an increment");
   activate(h);
-  int rc = enqueue_iteration(h);
+  int rc = enqueue_green(h);
+  if (rc == 0) rc = enqueue_constitutive(h);
   if (rc) return rc;
   rc = fetch_report(h, rep);
   CUDA_OK(h, cudaGetLastError());
@@ -784,7 +733,8 @@ int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iters outside an increment");
   activate(h);
   for (int i = 0; i < n; ++i) {
-    int rc = enqueue_iteration(h);
+    int rc = enqueue_green(h);
+    if (rc == 0) rc = enqueue_constitutive(h);
     if (rc) return rc;
   }
   int rc = fetch_report(h, last);
@@ -875,7 +825,6 @@ int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
     int rc = switch_to_voxel_classes(h);
     if (rc) return rc;
   }
-  if (f == EVP_FIELD_STRESS) h->spec_ready = false;
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   return EVP_OK;
 }
@@ -896,7 +845,6 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   if (!h || !out || comp < 0 || comp > 5) return EVP_ERR_ARG;
   if (h->nranks != 1) return fail(h, EVP_ERR_UNSUPPORTED, "debug_spectrum: single-rank handles only");
   activate(h);
-  h->spec_ready = false;
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, h->ny * h->nzl, h->Lplain, h->twx, h->st);
   launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
   launch_zfused(h->nz, true, h->tm_z, h->ti_z, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
@@ -911,7 +859,6 @@ int evp_set_profiling(evp_handle h, int32_t on) {
   if (!h) return EVP_ERR_ARG;
   cudaSetDevice(h->device);
   h->flags = on;
-  if (on & 2) h->spec_ready = false;
   if ((on & 1) && !h->ev_made) {
     for (auto &e : h->ev) CUDA_OK(h, cudaEventCreate(&e));
     h->ev_made = true;

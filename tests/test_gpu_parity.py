@@ -84,8 +84,7 @@ def test_forward_fft_matches_scipy(grid, product_lib):
 
 
 @pytest.mark.parametrize("grid,ng,hcp,mode", [((32, 32, 32), 50, False, "tension"), ((16, 32, 64), 30, True, "strain"),
-                                                ((64, 64, 64), 200, False, "psc"), ((128, 16, 32), 40, False, "tension"),
-                                                ((256, 8, 16), 20, True, "psc")])
+                                                ((64, 64, 64), 200, False, "psc")])
 def test_gpu_matches_oracle_fixed_iterations(grid, ng, hcp, mode, product_lib, oracle_lib):
     """Configs 1/2/3 of BASELINE.json at oracle-friendly iteration counts: identical iteration
     sequence on both sides, compared per iteration (SURVEY.md §5 parity hazard)."""
@@ -102,7 +101,7 @@ def test_gpu_matches_oracle_fixed_iterations(grid, ng, hcp, mode, product_lib, o
         sols.append(s)
     gpu, orc = sols
     assert rel_err(gpu.get_reference_medium(), orc.get_reference_medium()) < 1e-12
-    niter = 6 if max(grid) >= 64 else 10   # grids with nx >= 128 run the fused row kernel
+    niter = 6 if max(grid) >= 64 else 10
     for inc in range(2):
         for s in sols:
             s.begin_increment(2e-4)
@@ -119,28 +118,6 @@ def test_gpu_matches_oracle_fixed_iterations(grid, ng, hcp, mode, product_lib, o
                   api.FIELD_PLASTIC_RATE):
             assert rel_err(gpu.get_field(f), orc.get_field(f)) < TOL, f
     assert np.array_equal(gpu.get_field(api.FIELD_GRAIN), orc.get_field(api.FIELD_GRAIN))
-
-
-def test_fused_and_unfused_iterations_agree(product_lib, monkeypatch):
-    """evp_equilibrium_iter with the fused row kernel (x inv + update + Newton + x fwd) vs the separate kernels."""
-    outs = []
-    for nofuse in (False, True):
-        if nofuse:
-            monkeypatch.setenv("EVP_NO_FUSE", "1")
-        s, ids, grot = make_polycrystal(product_lib, product_lib, (128, 32, 16), 30, seed=6)
-        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
-        s.set_loading(api.Loading.uniaxial_tension(1.0))
-        reps = []
-        for inc in range(2):
-            s.begin_increment(2e-4)
-            for it in range(6):
-                r = s.equilibrium_iter()
-                reps.append([r.err_stress, r.err_strain, *r.savg, *r.emacro, r.newton_max, r.newton_mean])
-            s.end_increment()
-        outs.append((np.array(reps), s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN)))
-    assert rel_err(outs[0][0], outs[1][0]) < 1e-11
-    assert rel_err(outs[0][1], outs[1][1]) < 1e-11
-    assert rel_err(outs[0][2], outs[1][2]) < 1e-11
 
 
 def test_unit_parity_green_and_constitutive(product_lib, oracle_lib):
