@@ -119,14 +119,32 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__
   const double *b = a + N;
   const int nrl = min(C::L, nrows - row0);
   // coalesced load of L consecutive rows of both fields
-  for (int idx = tid * 2; idx < nrl * NX; idx += C::T * 2) {
-    const int l = idx / NX, x = idx % NX;
-    const double2 av = *reinterpret_cast<const double2 *>(a + idx);
-    const double2 bv = *reinterpret_cast<const double2 *>(b + idx);
-    sm[l * C::LS + x] = make_double2(av.x, bv.x);
-    sm[l * C::LS + x + 1] = make_double2(av.y, bv.y);
+  if (nrl == C::L) {   // full tile: compile-time trip count, every load issued before the first use
+    constexpr int NIT = C::L * NX / (2 * C::T);
+    double2 av[NIT], bv[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = (tid + it * C::T) * 2;
+      av[it] = *reinterpret_cast<const double2 *>(a + idx);
+      bv[it] = *reinterpret_cast<const double2 *>(b + idx);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = (tid + it * C::T) * 2;
+      const int l = idx / NX, x = idx % NX;
+      sm[l * C::LS + x] = make_double2(av[it].x, bv[it].x);
+      sm[l * C::LS + x + 1] = make_double2(av[it].y, bv[it].y);
+    }
+  } else {
+    for (int idx = tid * 2; idx < nrl * NX; idx += C::T * 2) {
+      const int l = idx / NX, x = idx % NX;
+      const double2 av = *reinterpret_cast<const double2 *>(a + idx);
+      const double2 bv = *reinterpret_cast<const double2 *>(b + idx);
+      sm[l * C::LS + x] = make_double2(av.x, bv.x);
+      sm[l * C::LS + x + 1] = make_double2(av.y, bv.y);
+    }
+    for (int idx = nrl * NX + tid; idx < C::L * NX; idx += C::T) sm[(idx / NX) * C::LS + idx % NX] = make_double2(0.0, 0.0);
   }
-  for (int idx = nrl * NX + tid; idx < C::L * NX; idx += C::T) sm[(idx / NX) * C::LS + idx % NX] = make_double2(0.0, 0.0);
   __syncthreads();
   const int l = tid % C::L, q = tid / C::L;
   block_fft<NX, false>(sm, q, OffES<1>{l * C::LS}, TwLdg{twp});
@@ -181,6 +199,27 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
   const double dEa = macro->dEpend[2 * pair], dEb = macro->dEpend[2 * pair + 1];
   double *ea = e + (long long)(2 * pair) * N + (long long)row0 * NX;
   double *eb = ea + N;
+  if (nrl == C::L && !de_dbg) {   // full tile: all e loads in flight before the first use
+    constexpr int NIT = C::L * NX / (2 * C::T);
+    double2 va[NIT], vb[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = (tid + it * C::T) * 2;
+      va[it] = *reinterpret_cast<double2 *>(ea + idx);
+      vb[it] = *reinterpret_cast<double2 *>(eb + idx);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = (tid + it * C::T) * 2;
+      const int ll = idx / NX, x = idx % NX;
+      const double2 z0 = sm[ll * C::LS + x], z1 = sm[ll * C::LS + x + 1];
+      va[it].x += dEa - z0.x; va[it].y += dEa - z1.x;
+      vb[it].x += dEb - z0.y; vb[it].y += dEb - z1.y;
+      *reinterpret_cast<double2 *>(ea + idx) = va[it];
+      *reinterpret_cast<double2 *>(eb + idx) = vb[it];
+    }
+    return;
+  }
   for (int idx = tid * 2; idx < nrl * NX; idx += C::T * 2) {
     const int ll = idx / NX, x = idx % NX;
     const double2 z0 = sm[ll * C::LS + x], z1 = sm[ll * C::LS + x + 1];

@@ -84,7 +84,8 @@ def test_forward_fft_matches_scipy(grid, product_lib):
 
 
 @pytest.mark.parametrize("grid,ng,hcp,mode", [((32, 32, 32), 50, False, "tension"), ((16, 32, 64), 30, True, "strain"),
-                                                ((64, 64, 64), 200, False, "psc")])
+                                                ((64, 64, 64), 200, False, "psc"), ((128, 16, 32), 40, False, "tension"),
+                                                ((256, 8, 16), 20, True, "psc")])
 def test_gpu_matches_oracle_fixed_iterations(grid, ng, hcp, mode, product_lib, oracle_lib):
     """Configs 1/2/3 of BASELINE.json at oracle-friendly iteration counts: identical iteration
     sequence on both sides, compared per iteration (SURVEY.md §5 parity hazard)."""
