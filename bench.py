@@ -59,7 +59,7 @@ def algorithmic_bytes(grid, nsys):
         "z_fused": 192 * Nc,
         "y_inv": 192 * Nc,
         "x_inv_update": 96 * Nc + 96 * N,   # read spectra, read+write e
-        "constitutive": (33 + nsys) * 8 * N + 4 * N,   # sig r/w, e, eps_p, crss, rot, phase id
+        "constitutive": (24 + nsys) * 8 * N + 4 * N,   # sig read+write, e, eps_p, 1/tau_c, orientation class id
     }
 
 
@@ -288,8 +288,14 @@ def main():
         kern.append({"name": k, "ms": round(float(kms[i]), 4), "algorithmic_bytes": int(ab[k]), "gbs": round(gbs, 1),
                      "frac_hbm": round(gbs / hbm, 4)})
     dom = max(range(6), key=lambda i: kms[i])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if list(tj.get("grid", [])) == list(local_grid) and KNAMES[dom] in tj and args.workload == "fcc":
+            traffic = tj[KNAMES[dom]]["dram_bytes"]
     roof = {"kernel": KNAMES[dom], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s",
-            "frac": kern[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+            "frac": kern[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
             "note": "constitutive is fp64-pipe bound (DESIGN.md §4); its HBM fraction is reported for uniformity"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
