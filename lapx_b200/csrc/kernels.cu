@@ -109,13 +109,13 @@ struct XCfg {
 
 template <int NX>
 __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__ sig, double2 *__restrict__ W, long long N,
-                                                      int nrows, SpecLayout Lay, int ny, const double2 *__restrict__ twp) {
+                                                      int rowbase, int nrows, SpecLayout Lay, int ny, const double2 *__restrict__ twp) {
   using C = XCfg<NX>;
   extern __shared__ double2 sm[];
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * C::L;
   const int pair = blockIdx.y;
-  const double *a = sig + (long long)(2 * pair) * N + (long long)row0 * NX;
+  const double *a = sig + (long long)(2 * pair) * N + (long long)(rowbase + row0) * NX;   // rowbase: first row of this z-chunk
   const double *b = a + N;
   const int nrl = min(C::L, nrows - row0);
   // coalesced load of L consecutive rows of both fields
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__
 // ---------------------------------------------------------------------------------------------
 template <int NX>
 __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict__ W, double *__restrict__ e, double *__restrict__ de_dbg,
-                                                      const MacroDev *__restrict__ macro, long long N, int nrows, SpecLayout Lay, int ny,
-                                                      const double2 *__restrict__ twp) {
+                                                      const MacroDev *__restrict__ macro, long long N, int rowbase, int nrows, SpecLayout Lay,
+                                                      int ny, const double2 *__restrict__ twp) {
   using C = XCfg<NX>;
   extern __shared__ double2 sm[];
   const int tid = threadIdx.x;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
   const int l = tid % C::L, q = tid / C::L;
   block_fft<NX, true>(sm, q, OffES<1>{l * C::LS}, TwLdg{twp});
   const double dEa = macro->dEpend[2 * pair], dEb = macro->dEpend[2 * pair + 1];
-  double *ea = e + (long long)(2 * pair) * N + (long long)row0 * NX;
+  double *ea = e + (long long)(2 * pair) * N + (long long)(rowbase + row0) * NX;
   double *eb = ea + N;
   if (nrl == C::L && !de_dbg) {   // full tile: all e loads in flight before the first use
     constexpr int NIT = C::L * NX / (2 * C::T);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
     *reinterpret_cast<double2 *>(ea + idx) = va;
     *reinterpret_cast<double2 *>(eb + idx) = vb;
     if (de_dbg) {
-      double *da = de_dbg + (long long)(2 * pair) * N + (long long)row0 * NX;
+      double *da = de_dbg + (long long)(2 * pair) * N + (long long)(rowbase + row0) * NX;
       *reinterpret_cast<double2 *>(da + idx) = make_double2(z0.x, z1.x);
       *reinterpret_cast<double2 *>(da + N + idx) = make_double2(z0.y, z1.y);
     }
@@ -253,7 +253,7 @@ struct YCfg {
 // 5-D tensor [kx][y % nyl][zl][c][y / nyl], the plain layout is the same with nyl = ny.
 template <int NY, bool INV>
 __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
-                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out,
+                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out, int nzc,
                                                        const double2 *__restrict__ twp) {
   using C = YCfg<NY>;
   extern __shared__ __align__(128) double2 sm[];
@@ -267,9 +267,10 @@ __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ C
     tma::fence_mbar_init();
   }
   __syncthreads();
+  const int nzt = min(C::ZT, nzc - z0);   // planes of this tile that exist in the chunk
   if (tid == 0) {
-    tma::mbar_expect_tx(&bar, (uint32_t)C::smem);
-    for (int zt = 0; zt < C::ZT; ++zt)
+    tma::mbar_expect_tx(&bar, (uint32_t)(nzt * NY * C::TX * sizeof(double2)));
+    for (int zt = 0; zt < nzt; ++zt)
       for (int y0 = 0; y0 < NY; y0 += yc_in)
         tma::load5(sm + (zt * NY + y0) * C::TX, &tin, &bar, 2 * k0, y0 & ((1 << lg_nyl_in) - 1), z0 + zt, c, y0 >> lg_nyl_in);
   }
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ C
   tma::fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
-    for (int zt = 0; zt < C::ZT; ++zt)
+    for (int zt = 0; zt < nzt; ++zt)
       for (int y0 = 0; y0 < NY; y0 += yc_out)
         tma::store5(&tout, sm + (zt * NY + y0) * C::TX, 2 * k0, y0 & ((1 << lg_nyl_out) - 1), z0 + zt, c, y0 >> lg_nyl_out);
     tma::commit();
@@ -304,7 +305,7 @@ struct ZCfg {
 };
 
 template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; MODE 1: forward only (evp_debug_spectrum)
-__global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ CUtensorMap tz, int lg_nzl, int zc,
+__global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ ZMaps tz, int lg_nzl, int lg_nzc, int zc,
                                                                         int ky0, int nx, int ny, double rx, double ry, double rz,
                                                                         double scale, const double2 *__restrict__ twp) {
   using C = ZCfg<NZ>;
@@ -319,15 +320,16 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
     tma::fence_mbar_init();
   }
   __syncthreads();
-  // tile [c][z][TX] by TMA: one op per (component, chunk of zc planes); z-split (recv) layout = 5-D tensor
-  // [kx][yl][z % nzl][c][z / nzl]
+  // tile [c][z][TX] by TMA: one op per (component, run of zc planes).  Global z = r*nzl + i*nzc + zz with r the source
+  // rank, i the pipeline chunk and zz the plane inside the chunk; each chunk is its own 5-D tensor [kx][yl][zz][c][r]
   if (tid == 0) {
     tma::mbar_expect_tx(&bar, (uint32_t)C::smem);
 #pragma unroll 1
     for (int c = 0; c < 6; ++c)
 #pragma unroll 1
       for (int z0 = 0; z0 < NZ; z0 += zc)
-        tma::load5(sm + c * C::CS + z0 * C::TX, &tz, &bar, 2 * k0, yl, z0 & ((1 << lg_nzl) - 1), c, z0 >> lg_nzl);
+        tma::load5(sm + c * C::CS + z0 * C::TX, &tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], &bar, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c,
+                   z0 >> lg_nzl);
   }
   tma::mbar_wait(&bar, 0);
   const int cg = tid / C::TPC, t = tid % C::TPC;
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
     for (int c = 0; c < 6; ++c)
 #pragma unroll 1
       for (int z0 = 0; z0 < NZ; z0 += zc)
-        tma::store5(&tz, sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzl) - 1), c, z0 >> lg_nzl);
+        tma::store5(&tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c,
+                    z0 >> lg_nzl);
     tma::commit();
     tma::wait_read0();
   }
@@ -410,9 +413,10 @@ __device__ __forceinline__ int warp_max(int v) {
 // per-warp partial sums (no block barrier): lane 0 of every warp stores NV sums and one max into the
 // SoA partial buffer  partials[k * nw + warp]
 template <int NV>
-__device__ __forceinline__ void warp_partials_store(const double vals[NV], int vmax, double *__restrict__ partials, long long nw) {
+__device__ __forceinline__ void warp_partials_store(const double vals[NV], int vmax, double *__restrict__ partials, long long nw,
+                                                    long long gw0 = 0) {
   const int lane = threadIdx.x & 31;
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long gw = gw0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const double s = warp_sum(vals[k]);
@@ -458,7 +462,8 @@ __global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax) {
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
 // (tables addressed as c_phase[0], i.e. immediate constant-bank operands).
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
-__global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *__restrict__ partials, long long nw, int pf_dist) {
+__global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long long vbase, long long count, double *__restrict__ partials,
+                                                              long long nw, long long gw0, int pf_dist) {
   extern __shared__ double smd[];  // [21 Jb | 6 g | 6 s_old | nsmax 1/tau_c] x kCB
   const int tid = threadIdx.x;
   const long long v = (long long)blockIdx.x * kCB + tid;
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, double *
     vals[8] = (double)nit;
     vals[9] = (double)bad;
   }
-  warp_partials_store<10>(vals, nit, partials, nw);
+  warp_partials_store<10>(vals, nit, partials, nw, gw0);
 }
 
 // second stage of the reductions: fixed-order two-level sum of the warp partials (deterministic)
@@ -703,53 +708,54 @@ bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 
     default: break;              \
   }
 
-void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int nrows, SpecLayout L, const double2 *tw, cudaStream_t st) {
+void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int rowbase, int nrows, SpecLayout L, const double2 *tw,
+                 cudaStream_t st) {
   const int ny = L.nyl;  // plain layout: nyl == ny
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
     set_smem(C::smem, k_xfwd<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
-    k_xfwd<NX><<<grid, C::T, C::smem, st>>>(sig, W, N, nrows, L, ny, tw);                              \
+    k_xfwd<NX><<<grid, C::T, C::smem, st>>>(sig, W, N, rowbase, nrows, L, ny, tw);                     \
   }
   EVP_DISPATCH_N(nx, X_)
 #undef X_
 }
 
-void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int nrows, SpecLayout L,
-                 const double2 *tw, cudaStream_t st) {
+void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,
+                 SpecLayout L, const double2 *tw, cudaStream_t st) {
   const int ny = L.nyl;
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
     set_smem(C::smem, k_xinv<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
-    k_xinv<NX><<<grid, C::T, C::smem, st>>>(W, e, de_dbg, macro, N, nrows, L, ny, tw);                 \
+    k_xinv<NX><<<grid, C::T, C::smem, st>>>(W, e, de_dbg, macro, N, rowbase, nrows, L, ny, tw);        \
   }
   EVP_DISPATCH_N(nx, X_)
 #undef X_
 }
 
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzl,
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st) {
 #define Y_(NY)                                                                                        \
   {                                                                                                   \
     using C = YCfg<NY>;                                                                               \
-    dim3 grid((nxh + C::TX - 1) / C::TX, (nzl + C::ZT - 1) / C::ZT, 6);                               \
+    dim3 grid((nxh + C::TX - 1) / C::TX, (nzc + C::ZT - 1) / C::ZT, 6);                               \
     if (inv) {                                                                                        \
       set_smem(C::smem, k_ypass<NY, true>);                                                           \
-      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, tw); \
+      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_ypass<NY, false>);                                                          \
-      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, tw); \
+      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(ny, Y_)
 #undef Y_
 }
 
-void launch_zfused(int nz, bool fwd_only, const CUtensorMap &tz, TileInfo zi, int nxh, int nyl, int ky0, int nx, int ny, double dx,
-                   double dy, double dz, const double2 *tw, cudaStream_t st) {
+void launch_zfused(int nz, bool fwd_only, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx, int ny,
+                   double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
 #define Z_(NZ)                                                                                        \
@@ -758,10 +764,10 @@ void launch_zfused(int nz, bool fwd_only, const CUtensorMap &tz, TileInfo zi, in
     dim3 grid((nxh + C::TX - 1) / C::TX, nyl);                                                        \
     if (fwd_only) {                                                                                   \
       set_smem(C::smem, k_zfused<NZ, 1>);                                                             \
-      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, zi.lg, zi.chunk, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_zfused<NZ, 0>);                                                             \
-      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, zi.lg, zi.chunk, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(nz, Z_)
@@ -776,8 +782,8 @@ long long partial_doubles(long long N) { return 11 * num_warps(N); }
 int reduce_scratch_doubles() { return kRedBlocks * 16; }
 
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
-static void launch_const_t(const Fields &f, int nsmax, double *partials, cudaStream_t st) {
-  const int nb = (int)((f.N + kCB - 1) / kCB);
+static void launch_const_t(const Fields &f, long long vbase, long long count, int nsmax, double *partials, cudaStream_t st) {
+  const int nb = (int)((count + kCB - 1) / kCB);
   const size_t smem = (size_t)(33 + (nsmax > 0 ? nsmax : 1)) * kCB * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
@@ -787,22 +793,24 @@ static void launch_const_t(const Fields &f, int nsmax, double *partials, cudaStr
   }
   static int pf = -1;
   if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * MINB;   // prefetch distance in blocks (0 = off)
-  k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, partials, num_warps(f.N), pf > 0 ? pf : (1 << 30));
+  // partial slots: chunks are multiples of kCB voxels, so warp index = voxel / 32
+  k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32, pf > 0 ? pf : (1 << 30));
 }
 
 // variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
-void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st) {
+void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow,
+                         double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
   static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 3;   // tuning knob: resident blocks per SM
-  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 4) return launch_const_t<12, 9, true, 4>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 2) return launch_const_t<12, 9, true, 2>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 3>(f, nsmax, partials, st);
-  if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 3>(f, nsmax, partials, st);
-  if (one && uniform_ns == 24 && uniform_npow == 9) return launch_const_t<24, 9, true, 3>(f, nsmax, partials, st);
-  if (one && uniform_ns == 24 && uniform_npow == 19) return launch_const_t<24, 19, true, 3>(f, nsmax, partials, st);
-  if (one && uniform_ns == 24) return launch_const_t<24, -2, true, 3>(f, nsmax, partials, st);
-  return launch_const_t<0, -2, false, 3>(f, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 4) return launch_const_t<12, 9, true, 4>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 2) return launch_const_t<12, 9, true, 2>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 3>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 3>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 24 && uniform_npow == 9) return launch_const_t<24, 9, true, 3>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 24 && uniform_npow == 19) return launch_const_t<24, 19, true, 3>(f, vbase, count, nsmax, partials, st);
+  if (one && uniform_ns == 24) return launch_const_t<24, -2, true, 3>(f, vbase, count, nsmax, partials, st);
+  return launch_const_t<0, -2, false, 3>(f, vbase, count, nsmax, partials, st);
 }
 
 __global__ void k_voxel_classes(Fields f) {

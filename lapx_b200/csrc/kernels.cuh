@@ -61,18 +61,22 @@ void upload_green(const GreenConst &g);
 void upload_const_params(const ConstParams &p);
 
 // launches (all on `st`)
-void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int nrows, SpecLayout L, const double2 *tw, cudaStream_t st);
+void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int rowbase, int nrows, SpecLayout L, const double2 *tw,
+                 cudaStream_t st);
 // TMA tiling of one spectral-buffer view: rows (y or z) per op and log2 of the rows per rank chunk
 struct TileInfo { int lg, chunk; };
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzl,
+constexpr int kMaxChunks = 8;
+struct ZMaps { CUtensorMap m[kMaxChunks]; };   // one tensor map per pipeline chunk of the z-split buffer
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
-void launch_zfused(int nz, bool fwd_only, const CUtensorMap &tz, TileInfo zi, int nxh, int nyl, int ky0, int nx, int ny, double dx,
-                   double dy, double dz, const double2 *tw, cudaStream_t st);
+void launch_zfused(int nz, bool fwd_only, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx, int ny,
+                   double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
 int ypass_tx();
 int zpass_tx(int nz);
-void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int nrows, SpecLayout L,
-                 const double2 *tw, cudaStream_t st);
-void launch_constitutive(const Fields &f, int nsmax, int nphases, int uniform_ns, int uniform_npow, double *partials, cudaStream_t st);
+void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,
+                 SpecLayout L, const double2 *tw, cudaStream_t st);
+void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow,
+                         double *partials, cudaStream_t st);
 void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st);
 long long partial_doubles(long long N);
 int reduce_scratch_doubles();

@@ -38,6 +38,7 @@ struct Nccl {
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommSplit)(void *, int, int, void **, void *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 Nccl g_nccl;
@@ -60,6 +61,7 @@ bool load_nccl(std::string *err) {
   g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))sym("ncclRecv");
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
   g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+  g_nccl.CommSplit = (int (*)(void *, int, int, void **, void *))sym("ncclCommSplit");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.AllReduce) {
     *err = "libnccl lacks required symbols";
     return false;
@@ -88,9 +90,26 @@ struct evp_solver {
   MacroDev *d_macro = nullptr, *h_macro = nullptr;  // h_macro pinned
   double *d_partials = nullptr, *d_totals = nullptr, *d_scratch = nullptr;
   int uniform_ns = 0, uniform_npow = -2;
-  SpecLayout Lplain{}, Lsplit{};
-  CUtensorMap tm_y_plain{}, tm_y_split{}, tm_z{};   // TMA descriptors of the spectral buffers
-  TileInfo ti_y_plain{}, ti_y_split{}, ti_z{};
+  // The local slab is processed in `nchunks` z-chunks of nzc planes, each with its own sub-buffers, so that with
+  // ranks > 1 the all-to-alls of one chunk run (on the communication stream) under the kernels of the others.
+  struct Chunk {
+    int rowbase = 0;                 // first (z,y) row of the chunk
+    long long vbase = 0, count = 0;  // voxel range
+    double2 *WA = nullptr, *WB = nullptr;
+    CUtensorMap tm_y_plain{}, tm_y_split{};
+    cudaEvent_t ev_fwd = nullptr, ev_a1 = nullptr, ev_a2 = nullptr;
+  };
+  int nchunks = 1, nzc = 0;
+  Chunk ch[kMaxChunks];
+  ZMaps zmaps{};
+  SpecLayout Lplain{}, Lsplit{};     // per-chunk layouts (nzl := nzc)
+  TileInfo ti_y_plain{}, ti_y_split{};
+  int zrun = 0, lg_nzl = 0, lg_nzc = 0;
+  cudaStream_t stc = nullptr;        // communication stream
+  cudaEvent_t ev_k4 = nullptr, ev_it0 = nullptr, ev_it1 = nullptr;
+  bool green_inflight = false;       // forward FFT + Green + way-back exchange of the CURRENT stress already enqueued
+  void *comm2 = nullptr;             // second communicator for the small all-reduces (compute stream)
+  struct Timers { cudaEvent_t a[128], b[128]; int type[128]; cudaStream_t s[128]; int n = 0; bool made = false; } tm;
   double C0m[36]{}, S0m[36]{};
   ConstParams cp{};
   GreenConst green{};
@@ -102,8 +121,6 @@ struct evp_solver {
   double Et[6]{}, Edot_prev[6]{};
   double dt = 0;
   int flags = 0;  // bit0: kernel timing, bit1: keep strain increment
-  cudaEvent_t ev[10]{};
-  bool ev_made = false;
   double last_ms[8]{};
   void *comm = nullptr;
   std::string err;
@@ -193,61 +210,155 @@ int nccl_check(evp_handle h, int rc, const char *what) {
   return fail(h, EVP_ERR_DEVICE, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"));
 }
 
-// all-to-all of equal contiguous chunks (FFT transpose): grouped ncclSend/ncclRecv
-int all_to_all(evp_handle h, const double2 *send, double2 *recv) {
-  const size_t chunk = (size_t)h->Lsplit.dstride * sizeof(double2);
+// all-to-all of equal contiguous pieces (FFT transpose): grouped ncclSend/ncclRecv
+int all_to_all(evp_handle h, const double2 *send, double2 *recv, cudaStream_t st) {
+  const size_t piece = (size_t)h->Lsplit.dstride * sizeof(double2);
   int rc = g_nccl.GroupStart();
   for (int p = 0; p < h->nranks && rc == 0; ++p) {
-    rc = g_nccl.Send((const char *)send + (size_t)p * chunk, chunk, kNcclChar, p, h->comm, h->st);
-    if (rc == 0) rc = g_nccl.Recv((char *)recv + (size_t)p * chunk, chunk, kNcclChar, p, h->comm, h->st);
+    rc = g_nccl.Send((const char *)send + (size_t)p * piece, piece, kNcclChar, p, h->comm, st);
+    if (rc == 0) rc = g_nccl.Recv((char *)recv + (size_t)p * piece, piece, kNcclChar, p, h->comm, st);
   }
   const int rc2 = g_nccl.GroupEnd();
   return nccl_check(h, rc ? rc : rc2, "nccl all-to-all");
 }
 
-void rec(evp_handle h, int i) {
-  if ((h->flags & 1) && h->ev_made) cudaEventRecord(h->ev[i], h->st);
+// kernel timers: event pairs around every launch, summed per kernel type in fetch_report
+void tbeg(evp_handle h, int type, cudaStream_t st) {
+  if (!(h->flags & 1) || !h->tm.made || h->tm.n >= 128) return;
+  h->tm.type[h->tm.n] = type;
+  h->tm.s[h->tm.n] = st;
+  cudaEventRecord(h->tm.a[h->tm.n], st);
+}
+void tend(evp_handle h) {
+  if (!(h->flags & 1) || !h->tm.made || h->tm.n >= 128) return;
+  cudaEventRecord(h->tm.b[h->tm.n], h->tm.s[h->tm.n]);
+  h->tm.n += 1;
 }
 
-// rows a1+a2+a3
-int enqueue_green(evp_handle h) {
-  const int nrows = h->ny * h->nzl;
-  rec(h, 0);
-  launch_xfwd(h->nx, h->f.sig, h->WB, h->N, nrows, h->Lplain, h->twx, h->st);
-  rec(h, 1);
-  launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_split, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzl, h->twy, h->st);
-  rec(h, 2);
+// K2 + K3 of chunk i, then (ranks > 1) its forward all-to-all on the communication stream
+int enqueue_forward_chunk(evp_handle h, int i) {
+  evp_solver::Chunk &c = h->ch[i];
+  const int nrows = h->ny * h->nzc;
+  tbeg(h, 0, h->st);
+  launch_xfwd(h->nx, h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
+  tend(h);
+  tbeg(h, 1, h->st);
+  launch_ypass(h->ny, false, c.tm_y_plain, c.tm_y_split, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->st);
+  tend(h);
   if (h->nranks > 1) {
-    int rc = all_to_all(h, h->WA, h->WB);
+    cudaEventRecord(c.ev_fwd, h->st);
+    cudaStreamWaitEvent(h->stc, c.ev_fwd, 0);
+    tbeg(h, 6, h->stc);
+    int rc = all_to_all(h, c.WA, c.WB, h->stc);
+    tend(h);
     if (rc) return rc;
+    cudaEventRecord(c.ev_a1, h->stc);
   }
-  rec(h, 3);
-  launch_zfused(h->nz, false, h->tm_z, h->ti_z, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
-  rec(h, 4);
-  if (h->nranks > 1) {
-    int rc = all_to_all(h, h->WB, h->WA);
-    if (rc) return rc;
-  }
-  rec(h, 5);
-  launch_ypass(h->ny, true, h->tm_y_split, h->tm_y_plain, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  rec(h, 6);
-  launch_xinv(h->nx, h->WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, nrows, h->Lplain, h->twx, h->st);
-  rec(h, 7);
   return EVP_OK;
 }
 
-// rows a4+a5+a6+a7
-int enqueue_constitutive(evp_handle h) {
-  launch_constitutive(h->f, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->d_partials, h->st);
+// K4 over all chunks (needs every forward exchange), then the way-back all-to-all of every chunk
+int enqueue_z_and_back(evp_handle h) {
+  if (h->nranks > 1)
+    for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
+  tbeg(h, 2, h->st);
+  launch_zfused(h->nz, false, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz,
+                h->twz, h->st);
+  tend(h);
+  if (h->nranks > 1) {
+    cudaEventRecord(h->ev_k4, h->st);
+    cudaStreamWaitEvent(h->stc, h->ev_k4, 0);
+    for (int i = 0; i < h->nchunks; ++i) {
+      tbeg(h, 6, h->stc);
+      int rc = all_to_all(h, h->ch[i].WB, h->ch[i].WA, h->stc);
+      tend(h);
+      if (rc) return rc;
+      cudaEventRecord(h->ch[i].ev_a2, h->stc);
+    }
+  }
+  h->green_inflight = true;
+  return EVP_OK;
+}
+
+// K5 + K6 of chunk i (after its way-back exchange has landed)
+int enqueue_back_chunk(evp_handle h, int i) {
+  evp_solver::Chunk &c = h->ch[i];
+  if (h->nranks > 1) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
+  tbeg(h, 3, h->st);
+  launch_ypass(h->ny, true, c.tm_y_split, c.tm_y_plain, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzc, h->twy, h->st);
+  tend(h);
+  tbeg(h, 4, h->st);
+  launch_xinv(h->nx, c.WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase, h->ny * h->nzc, h->Lplain, h->twx,
+              h->st);
+  tend(h);
+  return EVP_OK;
+}
+
+void enqueue_const_chunk(evp_handle h, int i) {
+  tbeg(h, 5, h->st);
+  launch_constitutive(h->f, h->ch[i].vbase, h->ch[i].count, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->d_partials, h->st);
+  tend(h);
+}
+
+// rows a6 (second stage) + a7
+int enqueue_reduce_macro(evp_handle h) {
   launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals, h->st);
   if (h->nranks > 1) {
-    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, h->comm, h->st);
-    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, h->comm, h->st);
+    void *cm = h->comm2 ? h->comm2 : h->comm;
+    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, cm, h->st);
+    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, cm, h->st);
     if (rc) return nccl_check(h, rc, "nccl allreduce");
   }
   launch_macro(h->d_totals, h->d_macro, h->Ntot, h->st);
-  rec(h, 8);
   return EVP_OK;
+}
+
+// the stress was changed from outside / buffers get reused: drop whatever transform is in flight
+void invalidate_green(evp_handle h) {
+  if (h->green_inflight && h->stc) cudaStreamSynchronize(h->stc);
+  h->green_inflight = false;
+}
+
+int enqueue_forward_all(evp_handle h) {
+  for (int i = 0; i < h->nchunks; ++i) {
+    int rc = enqueue_forward_chunk(h, i);
+    if (rc) return rc;
+  }
+  return enqueue_z_and_back(h);
+}
+
+// rows a1+a2+a3 (unit-test entry): finish the Green step for the current stress
+int enqueue_green(evp_handle h) {
+  int rc = EVP_OK;
+  if (!h->green_inflight) rc = enqueue_forward_all(h);
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i);
+  h->green_inflight = false;
+  return rc;
+}
+
+// rows a4+a5+a6+a7 (unit-test entry)
+int enqueue_constitutive(evp_handle h) {
+  for (int i = 0; i < h->nchunks; ++i) enqueue_const_chunk(h, i);
+  return enqueue_reduce_macro(h);
+}
+
+// One iteration as the solver runs it.  Per chunk: way back (K5, K6), Newton (K1) and at once the forward
+// transform of the NEW stress (K2, K3, forward exchange), so the exchanges of chunk i overlap the kernels of
+// chunk i+1; then the reductions, and the z pass + way-back exchange that the next iteration will consume.
+int enqueue_iteration(evp_handle h) {
+  int rc = EVP_OK;
+  if ((h->flags & 1) && h->tm.made) { h->tm.n = 0; cudaEventRecord(h->ev_it0, h->st); }
+  if (!h->green_inflight) rc = enqueue_forward_all(h);
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) {
+    rc = enqueue_back_chunk(h, i);
+    if (rc) break;
+    enqueue_const_chunk(h, i);
+    rc = enqueue_forward_chunk(h, i);
+  }
+  if (rc == 0) rc = enqueue_reduce_macro(h);
+  if (rc == 0) rc = enqueue_z_and_back(h);
+  if ((h->flags & 1) && h->tm.made) cudaEventRecord(h->ev_it1, h->st);
+  return rc;
 }
 
 int fetch_report(evp_handle h, evp_iter_report *rep) {
@@ -264,13 +375,13 @@ int fetch_report(evp_handle h, evp_iter_report *rep) {
     rep->converged = (m.iter >= h->ctrl.itmin && m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
     rep->nonfinite = m.nonfinite;
   }
-  if ((h->flags & 1) && h->ev_made) {
+  if ((h->flags & 1) && h->tm.made) {
+    if (h->stc) cudaStreamSynchronize(h->stc);
     for (int i = 0; i < 8; ++i) h->last_ms[i] = 0;
     float ms;
-    auto dtm = [&](int a, int b) { return cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) == cudaSuccess ? (double)ms : 0.0; };
-    h->last_ms[0] = dtm(0, 1); h->last_ms[1] = dtm(1, 2); h->last_ms[6] = dtm(2, 3) + dtm(4, 5);
-    h->last_ms[2] = dtm(3, 4); h->last_ms[3] = dtm(5, 6); h->last_ms[4] = dtm(6, 7); h->last_ms[5] = dtm(7, 8);
-    h->last_ms[7] = dtm(0, 8);
+    for (int i = 0; i < h->tm.n; ++i)
+      if (cudaEventElapsedTime(&ms, h->tm.a[i], h->tm.b[i]) == cudaSuccess) h->last_ms[h->tm.type[i]] += ms;
+    if (cudaEventElapsedTime(&ms, h->ev_it0, h->ev_it1) == cudaSuccess) h->last_ms[7] = ms;
   }
   return m.nonfinite ? fail(h, EVP_ERR_NUMERIC, "Newton produced a non-finite value / bad pivot") : EVP_OK;
 }
@@ -408,29 +519,59 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   } else {
     S->WB = S->WA;
   }
-  S->Lplain.nyl = S->ny; S->Lplain.nzl = S->nzl; S->Lplain.nxp = S->nxp; S->Lplain.nxh = S->nxh;
+  // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
+  {
+    int want = (nranks > 1) ? (getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : 4) : 1;
+    want = std::max(1, std::min(want, (int)kMaxChunks));
+    while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->ny * S->nx) % 128 != 0)) want /= 2;
+    S->nchunks = want;
+    S->nzc = S->nzl / want;
+  }
+  S->Lplain.nyl = S->ny; S->Lplain.nzl = S->nzc; S->Lplain.nxp = S->nxp; S->Lplain.nxh = S->nxh;
   S->Lplain.zstride = (long long)S->ny * S->nxp;
-  S->Lplain.cstride = (long long)S->nzl * S->Lplain.zstride;
+  S->Lplain.cstride = (long long)S->nzc * S->Lplain.zstride;
   S->Lplain.dstride = 6 * S->Lplain.cstride;
-  S->Lsplit.nyl = S->nyl; S->Lsplit.nzl = S->nzl; S->Lsplit.nxp = S->nxp; S->Lsplit.nxh = S->nxh;
+  S->Lsplit.nyl = S->nyl; S->Lsplit.nzl = S->nzc; S->Lsplit.nxp = S->nxp; S->Lsplit.nxh = S->nxh;
   S->Lsplit.zstride = (long long)S->nyl * S->nxp;
-  S->Lsplit.cstride = (long long)S->nzl * S->Lsplit.zstride;
+  S->Lsplit.cstride = (long long)S->nzc * S->Lsplit.zstride;
   S->Lsplit.dstride = 6 * S->Lsplit.cstride;
-  S->Lplain.lg_nyl = ilog2i(S->ny); S->Lplain.lg_nzl = ilog2i(S->nzl);
-  S->Lsplit.lg_nyl = ilog2i(S->nyl); S->Lsplit.lg_nzl = ilog2i(S->nzl);
+  S->Lplain.lg_nyl = ilog2i(S->ny); S->Lplain.lg_nzl = ilog2i(S->nzc);
+  S->Lsplit.lg_nyl = ilog2i(S->nyl); S->Lsplit.lg_nzl = ilog2i(S->nzc);
+  S->lg_nzl = ilog2i(S->nzl); S->lg_nzc = ilog2i(S->nzc);
   {
     std::string e;
-    const int ycp = std::min(S->ny, 256), ycs = std::min(S->nyl, 256), zc = std::min(S->nzl, 256);
+    const int ycp = std::min(S->ny, 256), ycs = std::min(S->nyl, 256);
+    S->zrun = std::min(S->nzc, 256);
     S->ti_y_plain = {S->Lplain.lg_nyl, ycp};
     S->ti_y_split = {S->Lsplit.lg_nyl, ycs};
-    S->ti_z = {S->Lsplit.lg_nzl, zc};
-    // K2 -> WB (plain) -> K3 -> WA (split) -> [all-to-all -> WB] -> K4 -> [all-to-all -> WA] -> K5 -> WB (plain) -> K6
-    double2 *Wz = (nranks > 1) ? S->WB : S->WA;
-    if (!make_tmap(&S->tm_y_plain, S->WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) ||
-        !make_tmap(&S->tm_y_split, S->WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) ||
-        !make_tmap(&S->tm_z, Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, zc, &e)) {
-      evp_destroy(S);
-      return fail(nullptr, EVP_ERR_DEVICE, e);
+    const size_t csize = (size_t)6 * S->nzc * S->ny * S->nxp;   // complex elements per chunk sub-buffer
+    for (int i = 0; i < S->nchunks; ++i) {
+      evp_solver::Chunk &c = S->ch[i];
+      c.rowbase = i * S->nzc * S->ny;
+      c.vbase = (long long)c.rowbase * S->nx;
+      c.count = (long long)S->nzc * S->ny * S->nx;
+      c.WA = S->WA + (size_t)i * csize;
+      c.WB = S->WB + (size_t)i * csize;
+      // K2 -> WB (plain) -> K3 -> WA (split) -> [all-to-all -> WB] -> K4 in place -> [all-to-all -> WA] -> K5 -> WB (plain) -> K6
+      double2 *Wz = (nranks > 1) ? c.WB : c.WA;
+      if (!make_tmap(&c.tm_y_plain, c.WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) ||
+          !make_tmap(&c.tm_y_split, c.WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) ||
+          !make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, S->zrun, &e)) {
+        evp_destroy(S);
+        return fail(nullptr, EVP_ERR_DEVICE, e);
+      }
+      if (nranks > 1) {
+        CK(cudaEventCreateWithFlags(&c.ev_fwd, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_a1, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_a2, cudaEventDisableTiming));
+      }
+    }
+    for (int i = S->nchunks; i < kMaxChunks; ++i) S->zmaps.m[i] = S->zmaps.m[0];
+    CK(cudaEventCreate(&S->ev_it0));
+    CK(cudaEventCreate(&S->ev_it1));
+    if (nranks > 1) {
+      CK(cudaStreamCreateWithFlags(&S->stc, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&S->ev_k4, cudaEventDisableTiming));
     }
   }
   S->twx = make_twiddles(S->nx); S->twy = make_twiddles(S->ny); S->twz = make_twiddles(S->nz);
@@ -449,6 +590,8 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
     std::memcpy(id.b, dist->nccl_id, 128);
     const int rc = g_nccl.CommInitRank(&S->comm, nranks, id, rank);
     if (rc) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "ncclCommInitRank failed"); }
+    // separate communicator for the tiny norm all-reduces so that they do not queue behind the transposes
+    if (g_nccl.CommSplit && g_nccl.CommSplit(S->comm, 0, rank, &S->comm2, nullptr) != 0) S->comm2 = nullptr;
   }
   CK(cudaStreamSynchronize(S->st));
 #undef CK
@@ -462,6 +605,8 @@ int evp_destroy(evp_handle h) {
   if (g_active == h) g_active = nullptr;
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->stc) cudaStreamSynchronize(h->stc);
+  if (h->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm2);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
   cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc); cudaFree(h->f.orient); cudaFree(h->f.orient_rep);
@@ -471,7 +616,16 @@ int evp_destroy(evp_handle h) {
   cudaFree(h->twx); cudaFree(h->twy); cudaFree(h->twz);
   cudaFree(h->d_macro); cudaFree(h->d_partials); cudaFree(h->d_totals); cudaFree(h->d_scratch);
   if (h->h_macro) cudaFreeHost(h->h_macro);
-  if (h->ev_made) for (auto &e : h->ev) cudaEventDestroy(e);
+  if (h->tm.made) for (int i = 0; i < 128; ++i) { cudaEventDestroy(h->tm.a[i]); cudaEventDestroy(h->tm.b[i]); }
+  for (int i = 0; i < kMaxChunks; ++i) {
+    if (h->ch[i].ev_fwd) cudaEventDestroy(h->ch[i].ev_fwd);
+    if (h->ch[i].ev_a1) cudaEventDestroy(h->ch[i].ev_a1);
+    if (h->ch[i].ev_a2) cudaEventDestroy(h->ch[i].ev_a2);
+  }
+  if (h->ev_k4) cudaEventDestroy(h->ev_k4);
+  if (h->ev_it0) cudaEventDestroy(h->ev_it0);
+  if (h->ev_it1) cudaEventDestroy(h->ev_it1);
+  if (h->stc) cudaStreamDestroy(h->stc);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return EVP_OK;
@@ -555,6 +709,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   CUDA_OK(h, cudaGetLastError());
   h->have_micro = true; h->in_incr = false;
+  invalidate_green(h);
   return EVP_OK;
 }
 
@@ -610,6 +765,7 @@ int evp_set_reference_medium(evp_handle h, const double *c0) {
   build_green_const(h->C0m, h->S0m, G);
   h->green = G;
   h->have_c0 = true;
+  invalidate_green(h);   // the Green operator changed
   g_active = nullptr;
   activate(h);
   if (h->have_loading) {  // Mmac depends on C0
@@ -701,6 +857,7 @@ int evp_begin_increment(evp_handle h, double dt) {
 int evp_op_green(evp_handle h) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_green outside an increment");
   activate(h);
+  h->tm.n = 0;
   int rc = enqueue_green(h);
   if (rc) return rc;
   CUDA_OK(h, cudaStreamSynchronize(h->st));
@@ -711,6 +868,7 @@ int evp_op_green(evp_handle h) {
 int evp_op_constitutive(evp_handle h, evp_iter_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "op_constitutive outside an increment");
   activate(h);
+  invalidate_green(h);   // the stress is about to change outside the pipelined iteration
   int rc = enqueue_constitutive(h);
   if (rc) return rc;
   rc = fetch_report(h, rep);
@@ -721,8 +879,7 @@ int evp_op_constitutive(evp_handle h, evp_iter_report *rep) {
 int evp_equilibrium_iter(evp_handle h, evp_iter_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iter outside an increment");
   activate(h);
-  int rc = enqueue_green(h);
-  if (rc == 0) rc = enqueue_constitutive(h);
+  int rc = enqueue_iteration(h);
   if (rc) return rc;
   rc = fetch_report(h, rep);
   CUDA_OK(h, cudaGetLastError());
@@ -733,8 +890,7 @@ int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "equilibrium_iters outside an increment");
   activate(h);
   for (int i = 0; i < n; ++i) {
-    int rc = enqueue_green(h);
-    if (rc == 0) rc = enqueue_constitutive(h);
+    int rc = enqueue_iteration(h);
     if (rc) return rc;
   }
   int rc = fetch_report(h, last);
@@ -825,6 +981,7 @@ int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
     int rc = switch_to_voxel_classes(h);
     if (rc) return rc;
   }
+  if (f == EVP_FIELD_STRESS) invalidate_green(h);
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   return EVP_OK;
 }
@@ -845,9 +1002,10 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   if (!h || !out || comp < 0 || comp > 5) return EVP_ERR_ARG;
   if (h->nranks != 1) return fail(h, EVP_ERR_UNSUPPORTED, "debug_spectrum: single-rank handles only");
   activate(h);
-  launch_xfwd(h->nx, h->f.sig, h->WA, h->N, h->ny * h->nzl, h->Lplain, h->twx, h->st);
-  launch_ypass(h->ny, false, h->tm_y_plain, h->tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, true, h->tm_z, h->ti_z, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  invalidate_green(h);
+  launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
+  launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
+  launch_zfused(h->nz, true, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));
@@ -859,10 +1017,11 @@ int evp_set_profiling(evp_handle h, int32_t on) {
   if (!h) return EVP_ERR_ARG;
   cudaSetDevice(h->device);
   h->flags = on;
-  if ((on & 1) && !h->ev_made) {
-    for (auto &e : h->ev) CUDA_OK(h, cudaEventCreate(&e));
-    h->ev_made = true;
+  if ((on & 1) && !h->tm.made) {
+    for (int i = 0; i < 128; ++i) { CUDA_OK(h, cudaEventCreate(&h->tm.a[i])); CUDA_OK(h, cudaEventCreate(&h->tm.b[i])); }
+    h->tm.made = true;
   }
+  if (on & 2) invalidate_green(h);
   if ((on & 2) && !h->f.de) {
     CUDA_OK(h, cudaMalloc(&h->f.de, sizeof(double) * 6 * h->N));
     CUDA_OK(h, cudaMemset(h->f.de, 0, sizeof(double) * 6 * h->N));
