@@ -466,14 +466,15 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
                                                               long long nw, long long gw0, int pf_dist) {
   extern __shared__ double smd[];  // [21 Jb | 6 g | 6 s_old | nsmax 1/tau_c] x kCB
   const int tid = threadIdx.x;
-  const long long v = (long long)blockIdx.x * kCB + tid;
+  const long long vl = (long long)blockIdx.x * kCB + tid;   // index inside this z-chunk
+  const long long v = vbase + vl;
   const long long N = f.N;
   double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
   int nit = 0;
   // L2 prefetch of the per-voxel streams of the block that runs one residency wave later: with ~12 warps per SM
   // the loads below would otherwise expose DRAM latency (ncu: long-scoreboard stalls on their first use)
   {
-    const long long vp = ((long long)blockIdx.x + pf_dist) * kCB;
+    const long long vp = vbase + ((long long)blockIdx.x + pf_dist) * kCB;
     if (vp + kCB <= N) {
       const int nstream = 18 + ((NS_T > 0) ? NS_T : 0);
       if (tid < nstream) {
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
       }
     }
   }
-  if (v < N) {
+  if (vl < count) {
     const PhaseDev &P = ONEPH ? c_phase[0] : c_phase[f.phase[v]];
     const SmAcc jb{smd + tid}, gv{smd + 21 * kCB + tid}, so{smd + 27 * kCB + tid}, itc{smd + 33 * kCB + tid};
     const long long NO = f.norient;

@@ -521,7 +521,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   }
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
-    int want = (nranks > 1) ? (getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : 4) : 1;
+    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? 4 : 1);   // env: also on one rank (tests)
     want = std::max(1, std::min(want, (int)kMaxChunks));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->ny * S->nx) % 128 != 0)) want /= 2;
     S->nchunks = want;

@@ -1,0 +1,30 @@
+"""GPU (-m gpu): the z-chunked, pipelined iteration (used with ranks > 1 to overlap the FFT transposes) run on one
+GPU with EVP_CHUNKS = 2/4 must reproduce the unchunked solve."""
+import numpy as np
+import pytest
+
+from common import make_polycrystal, rel_err
+from lapx_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("grid,hcp", [((8, 8, 8), False), ((32, 32, 32), False), ((16, 16, 64), True), ((128, 16, 32), False)])
+def test_chunked_equals_unchunked(grid, hcp, product_lib, monkeypatch):
+    outs = {}
+    for chunks in (1, 2, 4):
+        monkeypatch.setenv("EVP_CHUNKS", str(chunks))
+        s, ids, grot = make_polycrystal(product_lib, product_lib, grid, 12, seed=3, hcp=hcp)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.uniaxial_tension(1.0))
+        reps = []
+        for inc in range(2):
+            s.begin_increment(2e-4)
+            for it in range(5):
+                r = s.equilibrium_iter()
+                reps.append([r.err_stress, r.err_strain, *r.savg, *r.emacro, r.newton_max, r.newton_mean])
+            s.end_increment()
+        outs[chunks] = (np.array(reps), s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN), s.get_field(api.FIELD_CRSS))
+    for chunks in (2, 4):
+        for a, b in zip(outs[chunks], outs[1]):
+            assert rel_err(a, b) < 1e-12, chunks
