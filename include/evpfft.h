@@ -191,7 +191,8 @@ int  evp_debug_spectrum(evp_handle h, int32_t comp, double *out_reim);
 void *evp_stream(evp_handle h);
 /* Device time in ms of each kernel of the last evp_equilibrium_iter (CUDA events):
  * [0]=x fwd [1]=y fwd [2]=z fused [3]=y inv [4]=x inv+update [5]=constitutive [6]=exchange
- * [7]=whole iteration.  Only filled when evp_set_profiling(h,1).                          */
+ * [7]=whole iteration.  Only filled when evp_set_profiling(h,1).  Flag bits: 1 = kernel timers,
+ * 2 = keep the strain increment field (EVP_FIELD_STRAIN_INCR), 4 = use the one-shot z kernel.      */
 int  evp_set_profiling(evp_handle h, int32_t on);
 int  evp_last_kernel_ms(evp_handle h, double ms[8]);
 

@@ -550,4 +550,70 @@ EVP_HD void pass_store(double2 *s, int q, double2 v[8], OFF off, TW tw) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// radix-16 Stockham passes (16 points per thread) for the persistent z kernel: N = 16*16 or 8*16,
+// two passes instead of three -> fewer shared-memory round trips (the z pass is shared-memory bound).
+// ---------------------------------------------------------------------------------------------
+// 16-point DFT as 4x4: in place, natural order out.  Forward W16 = exp(-i pi/8).
+template <bool INV>
+EVP_HD void bfly16(double2 *v) {
+  // step 1: DFT4 over n2 for every n1 (elements n1 + 4 n2) -> Y[n1][k2] at position n1 + 4 k2
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) {
+    double2 t[4] = {v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]};
+    bfly4<INV>(t);
+    v[n1] = t[0]; v[n1 + 4] = t[1]; v[n1 + 8] = t[2]; v[n1 + 12] = t[3];
+  }
+  // step 2: twiddles W16^(n1*k2)
+  constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos, sin(pi/8)
+  auto mulw = [](double2 a, double wr, double wi) {   // a * (wr - i wi) forward, a * (wr + i wi) inverse
+    return INV ? make_double2(a.x * wr - a.y * wi, a.x * wi + a.y * wr) : make_double2(a.x * wr + a.y * wi, a.y * wr - a.x * wi);
+  };
+  v[1 + 4] = mulw(v[1 + 4], c1, s1);                 // W16^1
+  v[1 + 8] = mulw(v[1 + 8], kRSQ2, kRSQ2);           // W16^2
+  v[1 + 12] = mulw(v[1 + 12], s1, c1);               // W16^3
+  v[2 + 4] = mulw(v[2 + 4], kRSQ2, kRSQ2);           // W16^2
+  v[2 + 8] = mul_mi<INV>(v[2 + 8]);                  // W16^4 = -i
+  v[2 + 12] = mulw(v[2 + 12], -kRSQ2, kRSQ2);        // W16^6
+  v[3 + 4] = mulw(v[3 + 4], s1, c1);                 // W16^3
+  v[3 + 8] = mulw(v[3 + 8], -kRSQ2, kRSQ2);          // W16^6
+  v[3 + 12] = mulw(v[3 + 12], -c1, -s1);             // W16^9 = -W16^1
+  // step 3: DFT4 over n1 for every k2 -> X[4 k1 + k2] at position k1 + 4 k2
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) bfly4<INV>(&v[4 * k2]);
+}
+
+// thread (q in [0, N/16)) loads its 16 points for a pass of radix R (16 or 8): butterfly b handles j = q + b*N/16
+template <int N, int R, class OFF>
+EVP_HD void pass16_load(const double2 *s, int q, double2 v[16], OFF off) {
+#pragma unroll
+  for (int b = 0; b < 16 / R; ++b) {
+    const int j = q + b * (N / 16);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b * R + r] = s[off(j + r * (N / R))];
+  }
+}
+// first pass (NS = 1, no twiddles) or second pass (NS = N/16, R = 16, hoisted twiddles tw[r] = W_N^(r*k), k = q)
+template <int N, int R, int NS, bool INV, class OFF>
+EVP_HD void pass16_store(double2 *s, int q, double2 v[16], OFF off, const double2 *tw) {
+#pragma unroll
+  for (int b = 0; b < 16 / R; ++b) {
+    const int j = q + b * (N / 16);
+    const int k = j % NS;
+    if (NS > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[b * R + r] = INV ? cmulc(v[b * R + r], tw[r]) : cmul(v[b * R + r], tw[r]);
+    }
+    if (R == 16) bfly16<INV>(&v[b * R]); else bfly8<INV>(&v[b * R]);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      // radix 16 leaves X[4 k1 + k2] at position k1 + 4 k2
+      const int xr = (R == 16) ? (4 * (r & 3) + (r >> 2)) : r;
+      s[off(base + xr * NS)] = v[b * R + r];
+    }
+  }
+}
+
 }  // namespace evp

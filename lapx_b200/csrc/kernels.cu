@@ -389,6 +389,138 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4, production form for nz = 128 / 256: PERSISTENT blocks, tiles double-buffered by TMA, two radix-16
+// Stockham passes per direction with the second-pass twiddles hoisted into registers for the whole kernel.
+// Per tile: 10 shared-memory round trips instead of 14 and no exposed load/store (ncu on the one-shot kernel:
+// 65 % LSU-shared wavefronts, 38 % of the HBM roofline).
+// ---------------------------------------------------------------------------------------------
+template <int NZ>
+struct Z2Cfg {
+  static constexpr int TX = (NZ >= 256) ? 4 : 8;
+  static constexpr int R1 = NZ / 16;                    // first-pass radix (16 or 8)
+  static constexpr int TPC = TX * NZ / 16;              // threads per component (64)
+  static constexpr int T = 6 * TPC;                     // all six components at once
+  static constexpr int CS = NZ * TX;
+  static constexpr size_t tile = (size_t)6 * CS * sizeof(double2);
+  static constexpr size_t smem = 2 * tile;
+};
+
+template <int NZ>
+__global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_constant__ ZMaps tz, int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
+                                                            int ny, double rx, double ry, double rz, double scale, int nkx, int ntiles,
+                                                            const double2 *__restrict__ twp) {
+  using C = Z2Cfg<NZ>;
+  extern __shared__ __align__(128) double2 sm[];
+  __shared__ uint64_t full[2];
+  const int tid = threadIdx.x;
+  const int nxh = nx / 2 + 1;
+  const int c = tid / C::TPC, t = tid % C::TPC;
+  const int col = t % C::TX, q = t / C::TX;             // q in [0, NZ/16)
+  // hoisted second-pass twiddles: W_NZ^(r*q*NZ/(R1*16)), r = 1..15
+  double2 tw[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) tw[r] = __ldg(twp + ((r * q * (NZ / (C::R1 * 16))) & (NZ - 1)));
+  if (tid == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](int tile, int buf) {
+    const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+    double2 *dst = sm + (size_t)buf * 6 * C::CS;
+    tma::mbar_expect_tx(&full[buf], (uint32_t)C::tile);
+#pragma unroll 1
+    for (int cc = 0; cc < 6; ++cc)
+#pragma unroll 1
+      for (int z0 = 0; z0 < NZ; z0 += zc)
+        tma::load5(dst + cc * C::CS + z0 * C::TX, &tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], &full[buf], 2 * k0, yl,
+                   z0 & ((1 << lg_nzc) - 1), cc, z0 >> lg_nzl);
+  };
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
+  int n = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++n) {
+    const int buf = n & 1;
+    double2 *s = sm + (size_t)buf * 6 * C::CS;
+    const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+    // prefetch the next tile into the other buffer (its previous store has been read out: wait_read0 below)
+    if (tid == 0 && tile + gridDim.x < ntiles) {
+      tma::wait_read0();
+      issue_load(tile + gridDim.x, buf ^ 1);
+    }
+    tma::mbar_wait(&full[buf], (n >> 1) & 1);
+    const OffES<C::TX> off{c * C::CS + col};
+    double2 v[16];
+    // forward: pass 1 (radix R1, no twiddles), pass 2 (radix 16)
+    pass16_load<NZ, C::R1>(s, q, v, off);
+    __syncthreads();
+    pass16_store<NZ, C::R1, 1, false>(s, q, v, off, tw);
+    __syncthreads();
+    pass16_load<NZ, 16>(s, q, v, off);
+    __syncthreads();
+    pass16_store<NZ, 16, C::R1, false>(s, q, v, off, tw);
+    __syncthreads();
+    // Green operator per frequency (row a2)
+    {
+      const int ky = ky0 + yl;
+      const int fy = (ky <= ny / 2) ? ky : ky - ny;
+      double *smd = reinterpret_cast<double *>(s);
+#pragma unroll 1
+      for (int idx = tid; idx < C::CS; idx += C::T) {
+        const int cc = idx % C::TX, kz = idx / C::TX;
+        const int kx = k0 + cc;
+        if (kx < nxh) {
+          const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
+          const double x = kx * rx, y = fy * ry, z = fz * rz;
+          const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
+          const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
+          double g[6];
+          if (!nyq && !zero) green_G(c_green, x, y, z, scale, g);
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            double lam[6], o[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) lam[a] = smd[2 * (a * C::CS + idx) + part];
+            if (zero) {
+#pragma unroll
+              for (int a = 0; a < 6; ++a) o[a] = 0.0;
+            } else if (nyq) {
+              green_nyquist(c_green, scale, lam, o);
+            } else {
+              green_apply(g, x, y, z, lam, o);
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) smd[2 * (a * C::CS + idx) + part] = o[a];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // inverse
+    pass16_load<NZ, C::R1>(s, q, v, off);
+    __syncthreads();
+    pass16_store<NZ, C::R1, 1, true>(s, q, v, off, tw);
+    __syncthreads();
+    pass16_load<NZ, 16>(s, q, v, off);
+    __syncthreads();
+    pass16_store<NZ, 16, C::R1, true>(s, q, v, off, tw);
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll 1
+      for (int cc = 0; cc < 6; ++cc)
+#pragma unroll 1
+        for (int z0 = 0; z0 < NZ; z0 += zc)
+          tma::store5(&tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], s + cc * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), cc,
+                      z0 >> lg_nzl);
+      tma::commit();
+    }
+  }
+  if (tid == 0) tma::wait_read0();
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: constitutive update (rows a4, a5, a6).  One thread per voxel, 128 threads per block.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCB = 128;
@@ -755,10 +887,27 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &t
 #undef Y_
 }
 
-void launch_zfused(int nz, bool fwd_only, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx, int ny,
-                   double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
+void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx,
+                   int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
+  static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16
+  if (!fwd_only && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    if (nz == 256) {
+      using C = Z2Cfg<256>;
+      const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
+      set_smem(C::smem, k_zfused2<256>);
+      k_zfused2<256><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+    } else {
+      using C = Z2Cfg<128>;
+      const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
+      set_smem(C::smem, k_zfused2<128>);
+      k_zfused2<128><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+    }
+    return;
+  }
 #define Z_(NZ)                                                                                        \
   {                                                                                                   \
     using C = ZCfg<NZ>;                                                                               \

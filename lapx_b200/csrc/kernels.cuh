@@ -69,8 +69,8 @@ constexpr int kMaxChunks = 8;
 struct ZMaps { CUtensorMap m[kMaxChunks]; };   // one tensor map per pipeline chunk of the z-split buffer
 void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
-void launch_zfused(int nz, bool fwd_only, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx, int ny,
-                   double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
+void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx,
+                   int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
 int ypass_tx();
 int zpass_tx(int nz);
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,

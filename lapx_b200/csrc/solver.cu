@@ -120,7 +120,7 @@ struct evp_solver {
   bool strain_ctl[6]{};
   double Et[6]{}, Edot_prev[6]{};
   double dt = 0;
-  int flags = 0;  // bit0: kernel timing, bit1: keep strain increment
+  int flags = 0;  // bit0: kernel timing, bit1: keep strain increment, bit2: one-shot z kernel instead of the persistent one
   double last_ms[8]{};
   void *comm = nullptr;
   std::string err;
@@ -262,8 +262,8 @@ int enqueue_z_and_back(evp_handle h) {
   if (h->nranks > 1)
     for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
   tbeg(h, 2, h->st);
-  launch_zfused(h->nz, false, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz,
-                h->twz, h->st);
+  launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx,
+                h->g.dy, h->g.dz, h->twz, h->st);
   tend(h);
   if (h->nranks > 1) {
     cudaEventRecord(h->ev_k4, h->st);
@@ -1005,7 +1005,7 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   invalidate_green(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
   launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, true, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_zfused(h->nz, true, true, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

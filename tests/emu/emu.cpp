@@ -61,7 +61,38 @@ int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig
 }  // namespace
 
 
+// two-pass radix-16 path of the persistent z kernel (N = 128: 8x16, N = 256: 16x16)
+template <int N, bool INV>
+void emu_fft16_n(double2 *s, int nlines, const double2 *twt) {
+  constexpr int R1 = N / 16;
+  std::vector<double2> regs((size_t)nlines * (N / 16) * 16);
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 16; ++q) pass16_load<N, R1>(s, q, &regs[((size_t)l * (N / 16) + q) * 16], OffLin{l * N});
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 16; ++q) pass16_store<N, R1, 1, INV>(s, q, &regs[((size_t)l * (N / 16) + q) * 16], OffLin{l * N}, nullptr);
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 16; ++q) pass16_load<N, 16>(s, q, &regs[((size_t)l * (N / 16) + q) * 16], OffLin{l * N});
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 16; ++q) {
+      double2 tw[16];
+      for (int r = 0; r < 16; ++r) tw[r] = twt[(r * q * (N / (R1 * 16))) % N];   // hoisted: k = q, NS = R1
+      pass16_store<N, 16, R1, INV>(s, q, &regs[((size_t)l * (N / 16) + q) * 16], OffLin{l * N}, tw);
+    }
+}
+
 extern "C" {
+
+int emu_fft16(int n, int inv, int nlines, double *data) {
+  std::vector<double2> tw(n);
+  for (int k = 0; k < n; ++k) {
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+    tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  double2 *s = reinterpret_cast<double2 *>(data);
+  if (n == 128) { if (inv) emu_fft16_n<128, true>(s, nlines, tw.data()); else emu_fft16_n<128, false>(s, nlines, tw.data()); return 0; }
+  if (n == 256) { if (inv) emu_fft16_n<256, true>(s, nlines, tw.data()); else emu_fft16_n<256, false>(s, nlines, tw.data()); return 0; }
+  return -1;
+}
 
 // in-place FFT of nlines contiguous lines of length n (interleaved re,im); same pass sequence as block_fft
 int emu_fft(int n, int inv, int nlines, double *data) {

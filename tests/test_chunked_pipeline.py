@@ -28,3 +28,20 @@ def test_chunked_equals_unchunked(grid, hcp, product_lib, monkeypatch):
     for chunks in (2, 4):
         for a, b in zip(outs[chunks], outs[1]):
             assert rel_err(a, b) < 1e-12, chunks
+
+
+@pytest.mark.parametrize("grid", [(16, 16, 128), (32, 8, 256), (8, 64, 128)])
+def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
+    """k_zfused2 (persistent, double-buffered, radix-16) vs k_zfused (one tile per block, radix-8 passes)."""
+    outs = []
+    for flags in (0, 4):
+        s, ids, grot = make_polycrystal(product_lib, product_lib, grid, 12, seed=5)
+        s.set_profiling(flags)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.uniaxial_tension(1.0))
+        s.begin_increment(2e-4)
+        for it in range(5):
+            r = s.equilibrium_iter()
+        outs.append((s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN), np.array(r.savg[:])))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) < 1e-11

@@ -34,6 +34,17 @@ def test_stockham_passes_match_numpy(emu, n, inv):
     assert np.abs(buf - ref).max() < 5e-13 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n", [128, 256])
+@pytest.mark.parametrize("inv", [0, 1])
+def test_radix16_passes_match_numpy(emu, n, inv):
+    rng = np.random.default_rng(3 * n + inv)
+    x = rng.normal(size=(3, n)) + 1j * rng.normal(size=(3, n))
+    buf = np.ascontiguousarray(x.copy())
+    assert emu.emu_fft16(n, inv, 3, buf.ctypes.data_as(C.c_void_p)) == 0
+    ref = np.fft.ifft(x, axis=1) * n if inv else np.fft.fft(x, axis=1)
+    assert np.abs(buf - ref).max() < 5e-13 * np.abs(ref).max()
+
+
 def _rand_rot(rng):
     q = rng.normal(size=4)
     q /= np.linalg.norm(q)
