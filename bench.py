@@ -277,6 +277,13 @@ def main():
     sig = s.get_field(api.FIELD_STRESS)
     t_down = time.perf_counter() - t0
 
+    if world > 1:
+        td.barrier()
+    transport = "p2p" if lib.evp_transport(s.h) == 1 else "nccl"
+    s.close()
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     hbm, peak_src = peaks()
@@ -303,7 +310,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{'x'.join(map(str, grid))} {args.workload.upper()} Voronoi polycrystal ({ngrains} grains), EVP "
                                f"uniaxial tension, mid-increment iterations, reference medium = Voigt average",
-                   "grid": list(grid), "decomposition": "single GPU" if world == 1 else f"z-slabs over {world} GPUs, NCCL all-to-all",
+                   "grid": list(grid), "decomposition": "single GPU" if world == 1 else (f"z-slabs over {world} GPUs, FFT transposes = " + ("TMA stores into peer memory (CUDA IPC over NVLink) fused into the y/z passes" if transport == "p2p" else "NCCL all-to-all") + ", 4 pipelined z-chunks"),
                    "l2": "inputs larger than L2 (no flush needed)", "newton_mean": rep.newton_mean, "tol_newton": TOL_NEWTON,
                    "setup": {"h2d_bytes": int(up_bytes), "h2d_seconds": round(t_up, 4), "d2h_stress_bytes": int(sig.nbytes),
                              "d2h_seconds": round(t_down, 4)}},

@@ -209,6 +209,8 @@ int  evp_phase_hcp(evp_phase *out, double covera, const double c5[5] /* C11 C12 
 int  evp_voronoi(const evp_grid *g, int32_t ngrains, uint64_t seed, int32_t z0, int32_t nzl,
                  int32_t *grain_out, double *grain_rot9_out);
 int  evp_nccl_unique_id(uint8_t id[128]);
+/* 0 = single rank or NCCL all-to-all, 1 = peer-memory TMA stores (CUDA IPC). */
+int  evp_transport(evp_handle h);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ ABI_SYMBOLS_COMMON = [
     "evp_equilibrium_iter", "evp_op_green", "evp_op_constitutive", "evp_end_increment",
     "evp_step", "evp_equilibrium_iters", "evp_field_components", "evp_get_field",
     "evp_set_field", "evp_get_macro", "evp_debug_spectrum", "evp_stream",
-    "evp_set_profiling", "evp_last_kernel_ms",
+    "evp_set_profiling", "evp_last_kernel_ms", "evp_transport",
 ]
 ABI_SYMBOLS_PRODUCT_ONLY = ["evp_phase_fcc", "evp_phase_hcp", "evp_voronoi", "evp_nccl_unique_id"]
 
@@ -134,6 +134,7 @@ def _proto(lib):
         "evp_stream": ([H], C.c_void_p),
         "evp_set_profiling": ([H, C.c_int32], C.c_int),
         "evp_last_kernel_ms": ([H, C.c_void_p], C.c_int),
+        "evp_transport": ([H], C.c_int),
         "evp_phase_fcc": ([P(Phase)] + [C.c_double] * 9, C.c_int),
         "evp_phase_hcp": ([P(Phase), C.c_double, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                            C.c_void_p, C.c_void_p], C.c_int),

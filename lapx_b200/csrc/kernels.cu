@@ -47,6 +47,7 @@ __device__ __forceinline__ void store5(const CUtensorMap *tm, const void *src, i
 }
 __device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }   // writes performed (peer stores)
 }  // namespace tma
 
 __constant__ PhaseDev c_phase[EVP_MAX_PHASES];
@@ -252,8 +253,8 @@ struct YCfg {
 // Tiles move by TMA: one op per (plane, chunk of yc rows); the split (all-to-all send) layout is the
 // 5-D tensor [kx][y % nyl][zl][c][y / nyl], the plain layout is the same with nyl = ny.
 template <int NY, bool INV>
-__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
-                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out, int nzc,
+__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ CUtensorMap tin, const __grid_constant__ PeerMaps tout,
+                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out, int nzc, int p2p,
                                                        const double2 *__restrict__ twp) {
   using C = YCfg<NY>;
   extern __shared__ __align__(128) double2 sm[];
@@ -282,9 +283,14 @@ __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ C
   if (tid == 0) {
     for (int zt = 0; zt < nzt; ++zt)
       for (int y0 = 0; y0 < NY; y0 += yc_out)
-        tma::store5(&tout, sm + (zt * NY + y0) * C::TX, 2 * k0, y0 & ((1 << lg_nyl_out) - 1), z0 + zt, c, y0 >> lg_nyl_out);
+      {
+          // p2p: the rows of destination rank d go straight into rank d's receive buffer over NVLink (TMA store on the
+          // peer mapping): the FFT transpose is fused into this kernel's store phase.  Otherwise: local send layout.
+          const int d = y0 >> lg_nyl_out;
+          tma::store5(&tout.m[p2p ? d : 0], sm + (zt * NY + y0) * C::TX, 2 * k0, y0 & ((1 << lg_nyl_out) - 1), z0 + zt, c, p2p ? 0 : d);
+      }
     tma::commit();
-    tma::wait_read0();
+    if (p2p) tma::wait_all0(); else tma::wait_read0();
   }
 }
 
@@ -305,7 +311,8 @@ struct ZCfg {
 };
 
 template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; MODE 1: forward only (evp_debug_spectrum)
-__global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ ZMaps tz, int lg_nzl, int lg_nzc, int zc,
+__global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo,
+                                                                        int p2p, int lg_nzl, int lg_nzc, int zc,
                                                                         int ky0, int nx, int ny, double rx, double ry, double rz,
                                                                         double scale, const double2 *__restrict__ twp) {
   using C = ZCfg<NZ>;
@@ -381,10 +388,15 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
     for (int c = 0; c < 6; ++c)
 #pragma unroll 1
       for (int z0 = 0; z0 < NZ; z0 += zc)
-        tma::store5(&tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c,
-                    z0 >> lg_nzl);
+      {
+        const int r = z0 >> lg_nzl, i = (z0 & ((1 << lg_nzl) - 1)) >> lg_nzc;
+        if (p2p)   // planes of rank r go straight into rank r's way-back buffer (peer mapping)
+          tma::store5(&tzo.m[r * kMaxChunksP2P + i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, 0);
+        else
+          tma::store5(&tz.m[i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, r);
+      }
     tma::commit();
-    tma::wait_read0();
+    if (p2p) tma::wait_all0(); else tma::wait_read0();
   }
 }
 
@@ -406,7 +418,8 @@ struct Z2Cfg {
 };
 
 template <int NZ>
-__global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_constant__ ZMaps tz, int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
+__global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
+                                                            int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
                                                             int ny, double rx, double ry, double rz, double scale, int nkx, int ntiles,
                                                             const double2 *__restrict__ twp) {
   using C = Z2Cfg<NZ>;
@@ -512,12 +525,17 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
       for (int cc = 0; cc < 6; ++cc)
 #pragma unroll 1
         for (int z0 = 0; z0 < NZ; z0 += zc)
-          tma::store5(&tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], s + cc * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), cc,
-                      z0 >> lg_nzl);
+        {
+          const int r = z0 >> lg_nzl, i = (z0 & ((1 << lg_nzl) - 1)) >> lg_nzc;
+          if (p2p)
+            tma::store5(&tzo.m[r * kMaxChunksP2P + i], s + cc * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), cc, 0);
+          else
+            tma::store5(&tz.m[i], s + cc * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), cc, r);
+        }
       tma::commit();
     }
   }
-  if (tid == 0) tma::wait_read0();
+  if (tid == 0) { if (p2p) tma::wait_all0(); else tma::wait_read0(); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -869,7 +887,7 @@ void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const Macr
 #undef X_
 }
 
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzc,
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st) {
 #define Y_(NY)                                                                                        \
   {                                                                                                   \
@@ -877,18 +895,19 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &t
     dim3 grid((nxh + C::TX - 1) / C::TX, (nzc + C::ZT - 1) / C::ZT, 6);                               \
     if (inv) {                                                                                        \
       set_smem(C::smem, k_ypass<NY, true>);                                                           \
-      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, tw); \
+      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? 1 : 0, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_ypass<NY, false>);                                                          \
-      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, tw); \
+      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? 1 : 0, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(ny, Y_)
 #undef Y_
 }
 
-void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx,
-                   int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
+void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p_, int lg_nzl, int lg_nzc, int zrun,
+                   int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
+  const int p2p = p2p_ ? 1 : 0;
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
   static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16
@@ -899,12 +918,12 @@ void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg
       using C = Z2Cfg<256>;
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
       set_smem(C::smem, k_zfused2<256>);
-      k_zfused2<256><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      k_zfused2<256><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
     } else {
       using C = Z2Cfg<128>;
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
       set_smem(C::smem, k_zfused2<128>);
-      k_zfused2<128><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      k_zfused2<128><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
     }
     return;
   }
@@ -914,10 +933,10 @@ void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg
     dim3 grid((nxh + C::TX - 1) / C::TX, nyl);                                                        \
     if (fwd_only) {                                                                                   \
       set_smem(C::smem, k_zfused<NZ, 1>);                                                             \
-      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_zfused<NZ, 0>);                                                             \
-      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(nz, Z_)

@@ -66,11 +66,15 @@ void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int rowbase
 // TMA tiling of one spectral-buffer view: rows (y or z) per op and log2 of the rows per rank chunk
 struct TileInfo { int lg, chunk; };
 constexpr int kMaxChunks = 8;
+constexpr int kMaxRanks = 8;
+constexpr int kMaxChunksP2P = 4;   // pipeline chunks when the transposes are peer-memory stores (maps are kernel parameters)
 struct ZMaps { CUtensorMap m[kMaxChunks]; };   // one tensor map per pipeline chunk of the z-split buffer
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const CUtensorMap &tout, TileInfo in, TileInfo out, int nxh, int nzc,
+struct PeerMaps { CUtensorMap m[kMaxRanks]; }; // y pass output: m[0] = local send layout, or one map per destination rank (p2p)
+struct ZOutMaps { CUtensorMap m[kMaxRanks * kMaxChunksP2P]; };   // z pass output in p2p mode: [destination rank][chunk]
+void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
-void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, int lg_nzl, int lg_nzc, int zrun, int nxh, int nyl, int ky0, int nx,
-                   int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
+void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p, int lg_nzl, int lg_nzc, int zrun,
+                   int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
 int ypass_tx();
 int zpass_tx(int nz);
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,

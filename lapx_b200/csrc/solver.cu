@@ -39,6 +39,7 @@ struct Nccl {
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*CommSplit)(void *, int, int, void **, void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 Nccl g_nccl;
@@ -62,6 +63,7 @@ bool load_nccl(std::string *err) {
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
   g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
   g_nccl.CommSplit = (int (*)(void *, int, int, void **, void *))sym("ncclCommSplit");
+  g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))sym("ncclAllGather");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.AllReduce) {
     *err = "libnccl lacks required symbols";
     return false;
@@ -97,6 +99,8 @@ struct evp_solver {
     long long vbase = 0, count = 0;  // voxel range
     double2 *WA = nullptr, *WB = nullptr;
     CUtensorMap tm_y_plain{}, tm_y_split{};
+    PeerMaps out_fwd{};              // forward y pass output: m[0] = local send layout, or one map per destination rank (p2p)
+    PeerMaps out_inv{};              // inverse y pass output: m[0] = local plain layout
     cudaEvent_t ev_fwd = nullptr, ev_a1 = nullptr, ev_a2 = nullptr;
   };
   int nchunks = 1, nzc = 0;
@@ -109,6 +113,13 @@ struct evp_solver {
   cudaEvent_t ev_k4 = nullptr, ev_it0 = nullptr, ev_it1 = nullptr;
   bool green_inflight = false;       // forward FFT + Green + way-back exchange of the CURRENT stress already enqueued
   void *comm2 = nullptr;             // second communicator for the small all-reduces (compute stream)
+  // peer-memory transport: the transposes are TMA stores into the other ranks' buffers (CUDA IPC mappings)
+  bool p2p = false;
+  double2 *WC = nullptr;             // p2p: receive buffer of the forward transpose (written by every rank's y pass)
+  double2 *peerWA[kMaxRanks]{}, *peerWC[kMaxRanks]{};
+  ZOutMaps zout{};
+  double *d_bar = nullptr;           // barrier payload
+  cudaEvent_t ev_b1 = nullptr;
   struct Timers { cudaEvent_t a[128], b[128]; int type[128]; cudaStream_t s[128]; int n = 0; bool made = false; } tm;
   double C0m[36]{}, S0m[36]{};
   ConstParams cp{};
@@ -242,8 +253,18 @@ int enqueue_forward_chunk(evp_handle h, int i) {
   tbeg(h, 0, h->st);
   launch_xfwd(h->nx, h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
   tend(h);
+  if (h->p2p) {
+    // y pass + forward transpose in one kernel (TMA stores into the peers' receive buffers), on the communication
+    // stream: NVLink-bound, it runs under the constitutive kernel of the next chunk
+    cudaEventRecord(c.ev_fwd, h->st);
+    cudaStreamWaitEvent(h->stc, c.ev_fwd, 0);
+    tbeg(h, 1, h->stc);
+    launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, true, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->stc);
+    tend(h);
+    return EVP_OK;
+  }
   tbeg(h, 1, h->st);
-  launch_ypass(h->ny, false, c.tm_y_plain, c.tm_y_split, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->st);
   tend(h);
   if (h->nranks > 1) {
     cudaEventRecord(c.ev_fwd, h->st);
@@ -257,13 +278,37 @@ int enqueue_forward_chunk(evp_handle h, int i) {
   return EVP_OK;
 }
 
+// cross-GPU barrier on a stream: everything the ranks enqueued before it (peer stores included) has completed when it returns
+int enqueue_barrier(evp_handle h, void *comm, cudaStream_t st) {
+  const int rc = g_nccl.AllReduce(h->d_bar, h->d_bar, 1, kNcclDouble, kNcclSum, comm, st);
+  return rc ? nccl_check(h, rc, "nccl barrier") : EVP_OK;
+}
+
 // K4 over all chunks (needs every forward exchange), then the way-back all-to-all of every chunk
 int enqueue_z_and_back(evp_handle h) {
+  if (h->p2p) {
+    // all forward transposes (every rank's y-pass stores) done -> z pass, whose TMA stores ARE the way-back transpose
+    tbeg(h, 6, h->stc);
+    int rc = enqueue_barrier(h, h->comm, h->stc);
+    tend(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ev_b1, h->stc);
+    cudaStreamWaitEvent(h->st, h->ev_b1, 0);
+    tbeg(h, 2, h->st);
+    launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+                  h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+    tend(h);
+    tbeg(h, 6, h->st);
+    rc = enqueue_barrier(h, h->comm2 ? h->comm2 : h->comm, h->st);
+    tend(h);
+    h->green_inflight = true;
+    return rc;
+  }
   if (h->nranks > 1)
     for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
   tbeg(h, 2, h->st);
-  launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx, h->ny, h->g.dx,
-                h->g.dy, h->g.dz, h->twz, h->st);
+  launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+                h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   tend(h);
   if (h->nranks > 1) {
     cudaEventRecord(h->ev_k4, h->st);
@@ -283,9 +328,9 @@ int enqueue_z_and_back(evp_handle h) {
 // K5 + K6 of chunk i (after its way-back exchange has landed)
 int enqueue_back_chunk(evp_handle h, int i) {
   evp_solver::Chunk &c = h->ch[i];
-  if (h->nranks > 1) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
+  if (h->nranks > 1 && !h->p2p) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
   tbeg(h, 3, h->st);
-  launch_ypass(h->ny, true, c.tm_y_split, c.tm_y_plain, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzc, h->twy, h->st);
   tend(h);
   tbeg(h, 4, h->st);
   launch_xinv(h->nx, c.WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase, h->ny * h->nzc, h->Lplain, h->twx,
@@ -519,10 +564,71 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   } else {
     S->WB = S->WA;
   }
+  if (nranks > 1) {
+    std::string e;
+    if (!load_nccl(&e)) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, e); }
+    Id128 id;
+    std::memcpy(id.b, dist->nccl_id, 128);
+    const int rc = g_nccl.CommInitRank(&S->comm, nranks, id, rank);
+    if (rc) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "ncclCommInitRank failed"); }
+    // separate communicator for the tiny norm all-reduces so that they do not queue behind the transposes
+    if (g_nccl.CommSplit && g_nccl.CommSplit(S->comm, 0, rank, &S->comm2, nullptr) != 0) S->comm2 = nullptr;
+  }
+  // transport of the FFT transposes: 0/auto = peer-memory TMA stores when CUDA IPC works, 1 = NCCL all-to-all, 2 = p2p required
+  if (nranks > 1) {
+    int tr = dist->transport;
+    if (const char *e = getenv("EVP_TRANSPORT")) tr = (std::string(e) == "nccl") ? 1 : (std::string(e) == "p2p" ? 2 : tr);
+    if (tr != 1) {
+      std::string why;
+      if (nranks > kMaxRanks) why = "too many ranks";
+      if (why.empty() && cudaMalloc(&S->WC, wbytes) != cudaSuccess) why = "cudaMalloc(WC) failed";
+      if (why.empty() && !g_nccl.AllGather) why = "ncclAllGather missing";
+      if (why.empty()) {
+        cudaMemsetAsync(S->WC, 0, wbytes, S->st);
+        cudaIpcMemHandle_t mine[2];
+        std::vector<cudaIpcMemHandle_t> all((size_t)2 * nranks);
+        char *d_h = nullptr;
+        const size_t hb = sizeof(mine);
+        if (cudaIpcGetMemHandle(&mine[0], S->WA) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], S->WC) != cudaSuccess) why = "cudaIpcGetMemHandle failed";
+        if (why.empty() && cudaMalloc(&d_h, hb * nranks) != cudaSuccess) why = "cudaMalloc failed";
+        if (why.empty()) {
+          cudaMemcpyAsync(d_h + hb * rank, mine, hb, cudaMemcpyHostToDevice, S->st);
+          if (g_nccl.AllGather(d_h + hb * rank, d_h, hb, kNcclChar, S->comm, S->st) != 0) why = "ncclAllGather failed";
+          cudaMemcpyAsync(all.data(), d_h, hb * nranks, cudaMemcpyDeviceToHost, S->st);
+          cudaStreamSynchronize(S->st);
+          cudaFree(d_h);
+        }
+        int ok = why.empty() ? 1 : 0;
+        for (int p = 0; p < nranks && ok; ++p) {
+          if (p == rank) { S->peerWA[p] = S->WA; S->peerWC[p] = S->WC; continue; }
+          if (cudaIpcOpenMemHandle((void **)&S->peerWA[p], all[2 * p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+              cudaIpcOpenMemHandle((void **)&S->peerWC[p], all[2 * p + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            why = "cudaIpcOpenMemHandle failed";
+            cudaGetLastError();
+          }
+        }
+        // every rank must take the same decision
+        double flag = ok ? 0.0 : 1.0, *d_f = nullptr;
+        cudaMalloc(&d_f, sizeof(double));
+        cudaMemcpy(d_f, &flag, sizeof(double), cudaMemcpyHostToDevice);
+        g_nccl.AllReduce(d_f, d_f, 1, kNcclDouble, kNcclSum, S->comm, S->st);
+        cudaMemcpyAsync(&flag, d_f, sizeof(double), cudaMemcpyDeviceToHost, S->st);
+        cudaStreamSynchronize(S->st);
+        cudaFree(d_f);
+        S->p2p = (flag == 0.0);
+        if (!S->p2p && why.empty()) why = "a peer could not map the buffers";
+      }
+      if (!S->p2p && tr == 2) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "peer-memory transport requested but unavailable: " + why); }
+    }
+    CK(cudaMalloc(&S->d_bar, sizeof(double)));
+    CK(cudaMemset(S->d_bar, 0, sizeof(double)));
+    CK(cudaEventCreateWithFlags(&S->ev_b1, cudaEventDisableTiming));
+  }
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
     int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? 4 : 1);   // env: also on one rank (tests)
-    want = std::max(1, std::min(want, (int)kMaxChunks));
+    want = std::max(1, std::min(want, (int)(S->p2p ? kMaxChunksP2P : kMaxChunks)));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->ny * S->nx) % 128 != 0)) want /= 2;
     S->nchunks = want;
     S->nzc = S->nzl / want;
@@ -553,10 +659,23 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
       c.WA = S->WA + (size_t)i * csize;
       c.WB = S->WB + (size_t)i * csize;
       // K2 -> WB (plain) -> K3 -> WA (split) -> [all-to-all -> WB] -> K4 in place -> [all-to-all -> WA] -> K5 -> WB (plain) -> K6
-      double2 *Wz = (nranks > 1) ? c.WB : c.WA;
-      if (!make_tmap(&c.tm_y_plain, c.WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) ||
-          !make_tmap(&c.tm_y_split, c.WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) ||
-          !make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, S->zrun, &e)) {
+      // p2p:  K2 -> WB (plain) -> K3 stores into every peer's WC -> K4 reads WC, stores into every peer's WA -> K5 -> WB -> K6
+      double2 *Wz = S->p2p ? S->WC + (size_t)i * csize : ((nranks > 1) ? c.WB : c.WA);
+      bool ok = make_tmap(&c.tm_y_plain, c.WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) &&
+                make_tmap(&c.tm_y_split, c.WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) &&
+                make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, S->zrun, &e);
+      for (int p = 0; p < kMaxRanks && ok; ++p) {
+        c.out_inv.m[p] = c.tm_y_plain;
+        c.out_fwd.m[p] = c.tm_y_split;
+        if (S->p2p && p < nranks) {
+          // my rows for destination p land in p's receive buffer at source slot `rank`
+          ok = make_tmap(&c.out_fwd.m[p], S->peerWC[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit, 1, ypass_tx(), ycs, 1, &e);
+          // my ky rows of p's planes land in p's way-back buffer at slot `rank`
+          if (ok) ok = make_tmap(&S->zout.m[p * kMaxChunksP2P + i], S->peerWA[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit,
+                                 1, zpass_tx(S->nz), 1, S->zrun, &e);
+        }
+      }
+      if (!ok) {
         evp_destroy(S);
         return fail(nullptr, EVP_ERR_DEVICE, e);
       }
@@ -583,16 +702,6 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   CK(cudaMalloc(&S->d_partials, sizeof(double) * (size_t)partial_doubles(N)));
   CK(cudaMalloc(&S->d_totals, sizeof(double) * 64));
   CK(cudaMalloc(&S->d_scratch, sizeof(double) * reduce_scratch_doubles()));
-  if (nranks > 1) {
-    std::string e;
-    if (!load_nccl(&e)) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, e); }
-    Id128 id;
-    std::memcpy(id.b, dist->nccl_id, 128);
-    const int rc = g_nccl.CommInitRank(&S->comm, nranks, id, rank);
-    if (rc) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "ncclCommInitRank failed"); }
-    // separate communicator for the tiny norm all-reduces so that they do not queue behind the transposes
-    if (g_nccl.CommSplit && g_nccl.CommSplit(S->comm, 0, rank, &S->comm2, nullptr) != 0) S->comm2 = nullptr;
-  }
   CK(cudaStreamSynchronize(S->st));
 #undef CK
   (void)h;
@@ -606,6 +715,14 @@ int evp_destroy(evp_handle h) {
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->stc) cudaStreamSynchronize(h->stc);
+  if (h->p2p) {
+    // the host synchronises the ranks before destroying handles (no collective here: a lone destroy must not hang);
+    // every iteration ends with a cross-GPU barrier, so no peer store targets this rank once its own stream is idle
+    for (int p = 0; p < h->nranks; ++p)
+      if (p != h->rank) { if (h->peerWA[p]) cudaIpcCloseMemHandle(h->peerWA[p]); if (h->peerWC[p]) cudaIpcCloseMemHandle(h->peerWC[p]); }
+  }
+  cudaFree(h->WC); cudaFree(h->d_bar);
+  if (h->ev_b1) cudaEventDestroy(h->ev_b1);
   if (h->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm2);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
@@ -638,6 +755,7 @@ int evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl) {
   return EVP_OK;
 }
 int evp_nsys_max(evp_handle h) { return h ? h->nsmax : EVP_ERR_ARG; }
+int evp_transport(evp_handle h) { return (h && h->p2p) ? 1 : 0; }
 void *evp_stream(evp_handle h) { return h ? (void *)h->st : nullptr; }
 
 int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *phase, const double *rot9) {
@@ -1004,8 +1122,8 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   activate(h);
   invalidate_green(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
-  launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].tm_y_plain, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, true, true, h->zmaps, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].out_inv, false, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
+  launch_zfused(h->nz, true, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

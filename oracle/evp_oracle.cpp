@@ -665,6 +665,7 @@ int evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl) {
   return EVP_OK;
 }
 int evp_nsys_max(evp_handle h) { return h ? h->nsmax : EVP_ERR_ARG; }
+int evp_transport(evp_handle) { return 0; }
 
 int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *phase, const double *rot9) {
   if (!h || !grain || !rot9) return fail(h, EVP_ERR_ARG, "set_microstructure: null pointer");

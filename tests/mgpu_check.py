@@ -31,6 +31,8 @@ def run(lib, grid, ng, hcp, dd, niter=6, nincs=2):
         s.end_increment()
     out = {"sig": s.get_field(api.FIELD_STRESS), "e": s.get_field(api.FIELD_STRAIN), "crss": s.get_field(api.FIELD_CRSS),
            "c0": s.get_reference_medium(), "reps": np.array(reps), "z0": s.z0, "nzl": s.nzl}
+    if dd is not None:
+        td.barrier()          # p2p transport: nobody frees a buffer a peer may still be writing to
     s.close()
     return out
 
