@@ -91,6 +91,8 @@ typedef struct {
   int32_t itmin;
   double  tol_newton;                   /* per-voxel Newton: |dsig| <= tol*|sig|  */
   int32_t newton_itmax;
+  int32_t update_texture;               /* commit: lattice rotation (macro spin + local FFT spin - plastic spin) */
+  int32_t update_twinning;              /* commit: twin fractions and PTR reorientation (Tome, Lebensohn, Kocks 1991) */
 } evp_ctrl;
 
 typedef struct {
@@ -113,6 +115,9 @@ typedef struct {
   double  emacro[6];
   double  epavg[6];                     /* <eps_plastic> after commit             */
   double  seconds;                      /* wall time of the increment             */
+  double  twin_acc;                     /* accumulated twin volume fraction F_acc */
+  double  twin_eff;                     /* reoriented volume fraction F_eff       */
+  int64_t reoriented;                   /* voxels reoriented by this commit (all ranks) */
 } evp_step_report;
 
 typedef enum {
@@ -126,7 +131,9 @@ typedef enum {
   EVP_FIELD_PHASE = 7,         /* 1  int32                                                      */
   EVP_FIELD_GAMMA_ACC = 8,     /* 1  fp64  accumulated shear                                    */
   EVP_FIELD_TWIN_FRACTION = 9, /* nsys_max fp64 accumulated twin volume fraction per system     */
-  EVP_FIELD_STRAIN_INCR = 10   /* 6  fp64  last Gamma*sigma correction (debug / tests)          */
+  EVP_FIELD_STRAIN_INCR = 10,  /* 6  fp64  last Gamma*sigma correction (debug / tests)          */
+  EVP_FIELD_LOCAL_ROTATION = 11,/* 3 fp64  local rotation fluctuation (w32,w13,w21) of the compatible strain field   */
+  EVP_FIELD_TWINNED = 12       /* 1  int32 1 = voxel has been reoriented by PTR                 */
 } evp_field;
 
 /* ---- life cycle ----------------------------------------------------------------------- */

@@ -28,8 +28,8 @@ PRODUCT_LIB = os.path.join(_HERE, "libevpfft_b200.so")
 # evp_field
 FIELD_STRESS, FIELD_STRAIN, FIELD_PLASTIC_STRAIN, FIELD_PLASTIC_RATE = 0, 1, 2, 3
 FIELD_CRSS, FIELD_ROTATION, FIELD_GRAIN, FIELD_PHASE, FIELD_GAMMA_ACC = 4, 5, 6, 7, 8
-FIELD_TWIN_FRACTION, FIELD_STRAIN_INCR = 9, 10
-_INT_FIELDS = (FIELD_GRAIN, FIELD_PHASE)
+FIELD_TWIN_FRACTION, FIELD_STRAIN_INCR, FIELD_LOCAL_ROTATION, FIELD_TWINNED = 9, 10, 11, 12
+_INT_FIELDS = (FIELD_GRAIN, FIELD_PHASE, FIELD_TWINNED)
 
 
 class EvpError(RuntimeError):
@@ -71,7 +71,8 @@ class Dist(C.Structure):
 class Ctrl(C.Structure):
     _fields_ = [("tol_stress", C.c_double), ("tol_strain", C.c_double),
                 ("itmax", C.c_int32), ("itmin", C.c_int32),
-                ("tol_newton", C.c_double), ("newton_itmax", C.c_int32)]
+                ("tol_newton", C.c_double), ("newton_itmax", C.c_int32),
+                ("update_texture", C.c_int32), ("update_twinning", C.c_int32)]
 
 
 class IterReport(C.Structure):
@@ -85,7 +86,7 @@ class StepReport(C.Structure):
     _fields_ = [("iters", C.c_int32), ("converged", C.c_int32),
                 ("err_stress", C.c_double), ("err_strain", C.c_double),
                 ("savg", C.c_double * 6), ("emacro", C.c_double * 6), ("epavg", C.c_double * 6),
-                ("seconds", C.c_double)]
+                ("seconds", C.c_double), ("twin_acc", C.c_double), ("twin_eff", C.c_double), ("reoriented", C.c_int64)]
 
 
 # every symbol include/evpfft.h declares; tests check both libraries against this list
@@ -285,8 +286,8 @@ class Solver:
         return out.reshape(6, 6)
 
     def set_control(self, tol_stress=1e-6, tol_strain=1e-6, itmax=100, itmin=1, tol_newton=1e-6,
-                    newton_itmax=100):
-        c = Ctrl(tol_stress, tol_strain, itmax, itmin, tol_newton, newton_itmax)
+                    newton_itmax=100, update_texture=0, update_twinning=0):
+        c = Ctrl(tol_stress, tol_strain, itmax, itmin, tol_newton, newton_itmax, int(update_texture), int(update_twinning))
         self._check(self.lib.evp_set_control(self.h, C.byref(c)))
 
     def set_loading(self, ld: Loading):

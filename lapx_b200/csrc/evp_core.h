@@ -108,6 +108,9 @@ struct PhaseDev {
   // hardening (commit kernel)
   double tau0[EVP_MAX_MODES], tau1[EVP_MAX_MODES], theta0[EVP_MAX_MODES], theta1[EVP_MAX_MODES];
   double hlat[EVP_MAX_MODES][EVP_MAX_MODES];
+  double nrm[EVP_MAX_SYS][3];     // unit plane normals (crystal frame): twin reorientation 2 n n^T - I
+  double itshear[EVP_MAX_SYS];    // 1 / characteristic twin shear of the system's mode (0 for slip)
+  double twin_thr1, twin_thr2;
 };
 
 EVP_HD constexpr int s5idx(int i, int j) { return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j)); }
@@ -452,6 +455,45 @@ EVP_HD void green_point(const GreenConst &G0, double x, double y, double z, bool
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) out[c] = make_double2(orr[c], oi[c]);
+}
+
+
+// Local rotation spectrum of a compatible strain spectrum (commit step, §8(f).1): axial (w32,w13,w21) of
+// skew(u (x) xi) = (e^.xi (x) xi - xi (x) e^.xi)/|xi|^2, applied to the real or imaginary part. e in order 11,22,33,23,13,12.
+EVP_HD void rot_apply(double x, double y, double z, double scale, const double e[6], double w[3]) {
+  const double t0 = e[0] * x + e[5] * y + e[4] * z;
+  const double t1 = e[5] * x + e[1] * y + e[3] * z;
+  const double t2 = e[4] * x + e[3] * y + e[2] * z;
+  const double s = scale / (x * x + y * y + z * z);
+  w[0] = (t2 * y - t1 * z) * s;
+  w[1] = (t0 * z - t2 * x) * s;
+  w[2] = (t1 * x - t0 * y) * s;
+}
+// R <- exp([w]x) R, w axial (w32,w13,w21), R row major
+EVP_HD void rotate_lattice(double R[9], const double w[3]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double a, b;
+  if (th < 1e-8) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; }
+  else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double Q[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double k2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) k2 += K[3 * i + k] * K[3 * k + j];
+      Q[3 * i + j] = ((i == j) ? 1.0 : 0.0) + a * K[3 * i + j] + b * k2;
+    }
+  double Rn[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rn[3 * i + j] = Q[3 * i] * R[j] + Q[3 * i + 1] * R[3 + j] + Q[3 * i + 2] * R[6 + j];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = Rn[k];
 }
 
 // ---------------------------------------------------------------------------------------------

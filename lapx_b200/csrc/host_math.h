@@ -136,7 +136,11 @@ inline void build_phase_dev(const evp_phase &in, PhaseDev &pd) {
     pd.alpha[s][0] = 0.5 * (b[2] * n[1] - n[2] * b[1]);
     pd.alpha[s][1] = 0.5 * (b[0] * n[2] - n[0] * b[2]);
     pd.alpha[s][2] = 0.5 * (b[1] * n[0] - n[1] * b[0]);
+    for (int k = 0; k < 3; ++k) pd.nrm[s][k] = n[k];
+    pd.itshear[s] = (in.twin[m] && in.twin_shear[m] > 0) ? 1.0 / in.twin_shear[m] : 0.0;
   }
+  pd.twin_thr1 = in.twin_thr1;
+  pd.twin_thr2 = in.twin_thr2;
   for (int m = 0; m < EVP_MAX_MODES; ++m) {
     pd.tau0[m] = in.tau0[m]; pd.tau1[m] = in.tau1[m]; pd.theta0[m] = in.theta0[m]; pd.theta1[m] = in.theta1[m];
     for (int m2 = 0; m2 < EVP_MAX_MODES; ++m2) pd.hlat[m][m2] = in.hlat[m][m2];

@@ -197,6 +197,16 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
   __syncthreads();
   const int l = tid % C::L, q = tid / C::L;
   block_fft<NX, true>(sm, q, OffES<1>{l * C::LS}, TwLdg{twp});
+  if (e == nullptr) {   // plain output (commit step: local rotation field) into de_dbg
+    double *da = de_dbg + (long long)(2 * pair) * N + (long long)(rowbase + row0) * NX;
+    for (int idx = tid * 2; idx < nrl * NX; idx += C::T * 2) {
+      const int ll = idx / NX, x = idx % NX;
+      const double2 z0 = sm[ll * C::LS + x], z1 = sm[ll * C::LS + x + 1];
+      *reinterpret_cast<double2 *>(da + idx) = make_double2(z0.x, z1.x);
+      *reinterpret_cast<double2 *>(da + N + idx) = make_double2(z0.y, z1.y);
+    }
+    return;
+  }
   const double dEa = macro->dEpend[2 * pair], dEb = macro->dEpend[2 * pair + 1];
   double *ea = e + (long long)(2 * pair) * N + (long long)(rowbase + row0) * NX;
   double *eb = ea + N;
@@ -310,7 +320,7 @@ struct ZCfg {
   static constexpr int T = CG * TPC;
 };
 
-template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; MODE 1: forward only (evp_debug_spectrum)
+template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; 1: forward only (evp_debug_spectrum); 2: fwd + local-rotation spectrum + inv
 __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo,
                                                                         int p2p, int lg_nzl, int lg_nzc, int zc,
                                                                         int ky0, int nx, int ny, double rx, double ry, double rz,
@@ -343,8 +353,9 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
   const int col = t % C::TX, q = t / C::TX;
 #pragma unroll 1
   for (int c = cg; c < 6; c += C::CG) block_fft<NZ, false>(sm, q, OffES<C::TX>{c * C::CS + col}, TwLdg{twp});
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 2) {
     // Green operator per frequency (row a2); real and imaginary parts are transformed one after the other
+    // (MODE 2, commit step: strain spectrum -> local rotation spectrum in components 0..2, zeros in 3..5)
     const int ky = ky0 + yl;
     const int fy = (ky <= ny / 2) ? ky : ky - ny;
 #pragma unroll 1
@@ -357,14 +368,18 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
         const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
         const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
         double g[6];
-        if (!nyq && !zero) green_G(c_green, x, y, z, scale, g);
+        if (MODE == 0 && !nyq && !zero) green_G(c_green, x, y, z, scale, g);
         double *smd = reinterpret_cast<double *>(sm);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
           double lam[6], o[6];
 #pragma unroll
           for (int c = 0; c < 6; ++c) lam[c] = smd[2 * (c * C::CS + idx) + part];
-          if (zero) {
+          if (MODE == 2) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) o[c] = 0.0;
+            if (!zero && !nyq) rot_apply(x, y, z, scale, lam, o);
+          } else if (zero) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) o[c] = 0.0;
           } else if (nyq) {
@@ -753,12 +768,21 @@ __device__ __forceinline__ double voce_tau(const PhaseDev &P, int m, double G) {
   return t0 + (t1 + h1 * G) * (1.0 - exp(-G * fabs(h0 / t1)));
 }
 
-__global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__restrict__ partials, long long nw) {
+struct CommitParams {
+  double dt;
+  double wapp[3];       // applied (macroscopic) spin, axial (w32,w13,w21)
+  int texture, twinning;
+};
+
+// per-increment commit (§8(f).1): eps_p += dt*edp(sig); extended Voce; twin fractions; lattice rotation
+//   dR = exp(dt*W_app + (w_local_new - w_local_old) - dt*W_plastic) with w_local from the FFT of the compatible strain
+__global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, double *__restrict__ partials, long long nw) {
   extern __shared__ double dg_sm[];  // [nsmax][kCB] |dgamma|
   const int tid = threadIdx.x;
   const long long v = (long long)blockIdx.x * kCB + tid;
   const long long N = f.N;
-  double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const double dt = cp.dt;
+  double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] sum of twin fractions, [2..7] eps_p
   if (v < N) {
     const PhaseDev &P = c_phase[f.phase[v]];
     double R[9], M[25], t[6], sb[6], sc[6];
@@ -775,7 +799,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__r
       for (int b = 0; b < 5; ++b) x += M[b * 5 + a] * sb[b];
       sc[a] = x;
     }
-    double edc[5] = {0, 0, 0, 0, 0}, dG = 0.0;
+    double edc[5] = {0, 0, 0, 0, 0}, dG = 0.0, wpc[3] = {0, 0, 0}, fsum = 0.0;
     const int ns = P.nsys;
     for (int s = 0; s < ns; ++s) {
       double tau = 0.0;
@@ -785,9 +809,16 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__r
       slip_rate(P, s, tau, 1.0 / f.crss[(long long)s * N + v], gd, dgd);
 #pragma unroll
       for (int c = 0; c < 5; ++c) edc[c] += gd * P.m[s][c];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wpc[k] += P.alpha[s][k] * gd;
       const double dg = fabs(gd) * dt;
       dg_sm[s * kCB + tid] = dg;
       dG += dg;
+      if (cp.twinning && P.twin[s]) {
+        const double fnew = f.twinf[(long long)s * N + v] + gd * dt * P.itshear[s];
+        f.twinf[(long long)s * N + v] = fnew;
+        fsum += fnew;
+      }
     }
     double eds[6];
 #pragma unroll
@@ -806,6 +837,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__r
       f.epsp[c * N + v] = ep;
       sums[2 + c] = ep;
     }
+    sums[0] = fsum;
     const double G0 = f.gacc[v];
     if (dG > 0.0) {
       for (int s = 0; s < ns; ++s) {
@@ -816,6 +848,55 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, double dt, double *__r
         f.crss[(long long)s * N + v] += dv * hs / dG;
       }
       f.gacc[v] = G0 + dG;
+    }
+    if (cp.texture) {
+      double dw[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double wps = R[3 * k] * wpc[0] + R[3 * k + 1] * wpc[1] + R[3 * k + 2] * wpc[2];   // plastic spin, sample frame
+        const double wn = f.de[k * N + v];                                                         // new local rotation (FFT)
+        dw[k] = dt * cp.wapp[k] + (wn - f.wrot[k * N + v]) - dt * wps;
+        f.wrot[k * N + v] = wn;
+      }
+      rotate_lattice(R, dw);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f.rot[k * N + v] = R[k];
+    }
+  }
+  warp_partials_store<10>(sums, 0, partials, nw);
+}
+
+// PTR (Tome, Lebensohn, Kocks 1991): a voxel whose predominant twin system exceeds thr1 + thr2*ratio (ratio = F_eff/F_acc)
+// takes the twin orientation R (2 n n^T - I); counts go to partial slot 0
+__global__ void __launch_bounds__(kCB) k_twin_reorient(Fields f, double ratio, double *__restrict__ partials, long long nw) {
+  const long long v = (long long)blockIdx.x * kCB + threadIdx.x;
+  const long long N = f.N;
+  double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (v < N && !f.twinned[v]) {
+    const PhaseDev &P = c_phase[f.phase[v]];
+    const double thr = P.twin_thr1 + P.twin_thr2 * ratio;
+    int best = -1;
+    double fb = 0.0;
+    for (int s = 0; s < P.nsys; ++s) {
+      if (!P.twin[s]) continue;
+      const double fs = f.twinf[(long long)s * N + v];
+      if (fs > fb) { fb = fs; best = s; }
+    }
+    if (best >= 0 && fb > thr) {
+      double R[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = f.rot[k * N + v];
+      const double n0 = P.nrm[best][0], n1 = P.nrm[best][1], n2 = P.nrm[best][2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double rn = R[3 * i] * n0 + R[3 * i + 1] * n1 + R[3 * i + 2] * n2;
+        f.rot[(3 * i) * N + v] = 2.0 * rn * n0 - R[3 * i];
+        f.rot[(3 * i + 1) * N + v] = 2.0 * rn * n1 - R[3 * i + 1];
+        f.rot[(3 * i + 2) * N + v] = 2.0 * rn * n2 - R[3 * i + 2];
+      }
+      for (int s = 0; s < P.nsys; ++s) f.twinf[(long long)s * N + v] = 0.0;
+      f.twinned[v] = 1;
+      sums[0] = 1.0;
     }
   }
   warp_partials_store<10>(sums, 0, partials, nw);
@@ -905,13 +986,14 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout
 #undef Y_
 }
 
-void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p_, int lg_nzl, int lg_nzc, int zrun,
+void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p_, int lg_nzl, int lg_nzc, int zrun,
                    int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
   const int p2p = p2p_ ? 1 : 0;
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
   static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16
-  if (!fwd_only && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {
+  const bool fwd_only = mode == 1;
+  if (mode == 0 && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
     if (nz == 256) {
@@ -934,6 +1016,9 @@ void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, const 
     if (fwd_only) {                                                                                   \
       set_smem(C::smem, k_zfused<NZ, 1>);                                                             \
       k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+    } else if (mode == 2) {                                                                           \
+      set_smem(C::smem, k_zfused<NZ, 2>);                                                             \
+      k_zfused<NZ, 2><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_zfused<NZ, 0>);                                                             \
       k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
@@ -996,10 +1081,15 @@ void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st) {
   k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax);
 }
 
-void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st) {
+void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st) {
   const int nb = (int)((f.N + kCB - 1) / kCB);
   const size_t smem = (size_t)(nsmax > 0 ? nsmax : 1) * kCB * sizeof(double);
-  k_commit<<<nb, kCB, smem, st>>>(f, dt, partials, num_warps(f.N));
+  CommitParams cp{dt, {wapp[0], wapp[1], wapp[2]}, texture, twinning};
+  k_commit<<<nb, kCB, smem, st>>>(f, cp, partials, num_warps(f.N));
+}
+void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaStream_t st) {
+  const int nb = (int)((f.N + kCB - 1) / kCB);
+  k_twin_reorient<<<nb, kCB, 0, st>>>(f, ratio, partials, num_warps(f.N));
 }
 
 void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) {

@@ -47,6 +47,8 @@ struct MacroDev {
 
 struct Fields {
   double *sig, *e, *epsp, *edotp, *crss, *rot, *gacc, *twinf, *de;
+  double *wrot;             // local rotation fluctuation (3) of the committed strain field
+  int32_t *twinned;         // PTR flag
   double *mrot, *jb, *itc;  // per-increment invariants: deviatoric rotation M (25), Jb = S0_c + S_c (21), 1/tau_c
   int32_t *grain, *phase;
   int32_t *orient;          // orientation class of every voxel (index into mrot/jb tables)
@@ -73,7 +75,7 @@ struct PeerMaps { CUtensorMap m[kMaxRanks]; }; // y pass output: m[0] = local se
 struct ZOutMaps { CUtensorMap m[kMaxRanks * kMaxChunksP2P]; };   // z pass output in p2p mode: [destination rank][chunk]
 void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
-void launch_zfused(int nz, bool fwd_only, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p, int lg_nzl, int lg_nzc, int zrun,
+void launch_zfused(int nz, int mode /* 0 Green, 1 forward only, 2 local rotation */, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p, int lg_nzl, int lg_nzc, int zrun,
                    int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
 int ypass_tx();
 int zpass_tx(int nz);
@@ -87,7 +89,8 @@ int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
 void launch_voxel_classes(const Fields &f, cudaStream_t st);
 void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st);
-void launch_commit(const Fields &f, int nsmax, double dt, double *partials, cudaStream_t st);
+void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st);
+void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaStream_t st);
 void launch_fill(double *p, long long n, double v, cudaStream_t st);
 void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st);
 bool fft_size_supported(int n);

@@ -125,7 +125,8 @@ struct evp_solver {
   ConstParams cp{};
   GreenConst green{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
-  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100};
+  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100, 0, 0};
+  long long ntwinned = 0;   // voxels reoriented by PTR so far (all ranks)
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};
   bool strain_ctl[6]{};
@@ -194,7 +195,8 @@ size_t field_comps(const evp_solver *S, int f) {
     case EVP_FIELD_PLASTIC_RATE: case EVP_FIELD_STRAIN_INCR: return 6;
     case EVP_FIELD_CRSS: case EVP_FIELD_TWIN_FRACTION: return (size_t)S->nsmax;
     case EVP_FIELD_ROTATION: return 9;
-    case EVP_FIELD_GRAIN: case EVP_FIELD_PHASE: case EVP_FIELD_GAMMA_ACC: return 1;
+    case EVP_FIELD_GRAIN: case EVP_FIELD_PHASE: case EVP_FIELD_GAMMA_ACC: case EVP_FIELD_TWINNED: return 1;
+    case EVP_FIELD_LOCAL_ROTATION: return 3;
     default: return 0;
   }
 }
@@ -210,6 +212,8 @@ void *field_ptr(evp_solver *S, int f, size_t *el) {
     case EVP_FIELD_GAMMA_ACC: return S->f.gacc;
     case EVP_FIELD_TWIN_FRACTION: return S->f.twinf;
     case EVP_FIELD_STRAIN_INCR: return S->f.de;
+    case EVP_FIELD_LOCAL_ROTATION: return S->f.wrot;
+    case EVP_FIELD_TWINNED: *el = sizeof(int32_t); return S->f.twinned;
     case EVP_FIELD_GRAIN: *el = sizeof(int32_t); return S->f.grain;
     case EVP_FIELD_PHASE: *el = sizeof(int32_t); return S->f.phase;
     default: return nullptr;
@@ -247,11 +251,11 @@ void tend(evp_handle h) {
 }
 
 // K2 + K3 of chunk i, then (ranks > 1) its forward all-to-all on the communication stream
-int enqueue_forward_chunk(evp_handle h, int i) {
+int enqueue_forward_chunk(evp_handle h, int i, const double *field = nullptr) {
   evp_solver::Chunk &c = h->ch[i];
   const int nrows = h->ny * h->nzc;
   tbeg(h, 0, h->st);
-  launch_xfwd(h->nx, h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
+  launch_xfwd(h->nx, field ? field : h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
   tend(h);
   if (h->p2p) {
     // y pass + forward transpose in one kernel (TMA stores into the peers' receive buffers), on the communication
@@ -285,7 +289,7 @@ int enqueue_barrier(evp_handle h, void *comm, cudaStream_t st) {
 }
 
 // K4 over all chunks (needs every forward exchange), then the way-back all-to-all of every chunk
-int enqueue_z_and_back(evp_handle h) {
+int enqueue_z_and_back(evp_handle h, int zmode = 0) {
   if (h->p2p) {
     // all forward transposes (every rank's y-pass stores) done -> z pass, whose TMA stores ARE the way-back transpose
     tbeg(h, 6, h->stc);
@@ -295,7 +299,7 @@ int enqueue_z_and_back(evp_handle h) {
     cudaEventRecord(h->ev_b1, h->stc);
     cudaStreamWaitEvent(h->st, h->ev_b1, 0);
     tbeg(h, 2, h->st);
-    launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
                   h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
     tend(h);
     tbeg(h, 6, h->st);
@@ -307,7 +311,7 @@ int enqueue_z_and_back(evp_handle h) {
   if (h->nranks > 1)
     for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
   tbeg(h, 2, h->st);
-  launch_zfused(h->nz, false, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+  launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
                 h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   tend(h);
   if (h->nranks > 1) {
@@ -326,15 +330,15 @@ int enqueue_z_and_back(evp_handle h) {
 }
 
 // K5 + K6 of chunk i (after its way-back exchange has landed)
-int enqueue_back_chunk(evp_handle h, int i) {
+int enqueue_back_chunk(evp_handle h, int i, bool plain = false) {
   evp_solver::Chunk &c = h->ch[i];
   if (h->nranks > 1 && !h->p2p) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
   tbeg(h, 3, h->st);
   launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzc, h->twy, h->st);
   tend(h);
   tbeg(h, 4, h->st);
-  launch_xinv(h->nx, c.WB, h->f.e, (h->flags & 2) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase, h->ny * h->nzc, h->Lplain, h->twx,
-              h->st);
+  launch_xinv(h->nx, c.WB, plain ? nullptr : h->f.e, (plain || (h->flags & 2)) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase,
+              h->ny * h->nzc, h->Lplain, h->twx, h->st);
   tend(h);
   return EVP_OK;
 }
@@ -364,12 +368,21 @@ void invalidate_green(evp_handle h) {
   h->green_inflight = false;
 }
 
-int enqueue_forward_all(evp_handle h) {
+int enqueue_forward_all(evp_handle h, const double *field = nullptr, int zmode = 0) {
   for (int i = 0; i < h->nchunks; ++i) {
-    int rc = enqueue_forward_chunk(h, i);
+    int rc = enqueue_forward_chunk(h, i, field);
     if (rc) return rc;
   }
-  return enqueue_z_and_back(h);
+  return enqueue_z_and_back(h, zmode);
+}
+
+// commit step: local rotation field (w32,w13,w21) of the compatible strain e into f.de[0..2] (same FFT chain, z mode 2)
+int enqueue_rotation_field(evp_handle h) {
+  invalidate_green(h);   // the chain reuses the spectral buffers
+  int rc = enqueue_forward_all(h, h->f.e, 2);
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i, true);
+  h->green_inflight = false;
+  return rc;
 }
 
 // rows a1+a2+a3 (unit-test entry): finish the Green step for the current stress
@@ -550,6 +563,8 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   CK(cudaMalloc(&S->f.rot, sizeof(double) * 9 * N));
   CK(cudaMalloc(&S->f.gacc, sizeof(double) * N));
   CK(cudaMalloc(&S->f.orient, sizeof(int32_t) * N));
+  CK(cudaMalloc(&S->f.wrot, sizeof(double) * 3 * N));
+  CK(cudaMalloc(&S->f.twinned, sizeof(int32_t) * N));
   CK(cudaMalloc(&S->f.itc, sizeof(double) * ns * N));
   if (any_twin) CK(cudaMalloc(&S->f.twinf, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.grain, sizeof(int32_t) * N));
@@ -727,6 +742,7 @@ int evp_destroy(evp_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
   cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc); cudaFree(h->f.orient); cudaFree(h->f.orient_rep);
+  cudaFree(h->f.wrot); cudaFree(h->f.twinned);
   cudaFree(h->f.rot); cudaFree(h->f.gacc); cudaFree(h->f.twinf); cudaFree(h->f.de); cudaFree(h->f.grain); cudaFree(h->f.phase);
   if (h->WB && h->WB != h->WA) cudaFree(h->WB);
   cudaFree(h->WA);
@@ -813,6 +829,9 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   CUDA_OK(h, cudaMemsetAsync(h->f.epsp, 0, sizeof(double) * 6 * N, h->st));
   CUDA_OK(h, cudaMemsetAsync(h->f.edotp, 0, sizeof(double) * 6 * N, h->st));
   CUDA_OK(h, cudaMemsetAsync(h->f.gacc, 0, sizeof(double) * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.wrot, 0, sizeof(double) * 3 * N, h->st));
+  CUDA_OK(h, cudaMemsetAsync(h->f.twinned, 0, sizeof(int32_t) * N, h->st));
+  h->ntwinned = 0;
   if (h->f.twinf) CUDA_OK(h, cudaMemsetAsync(h->f.twinf, 0, sizeof(double) * std::max(h->nsmax, 1) * N, h->st));
   if (h->f.de) CUDA_OK(h, cudaMemsetAsync(h->f.de, 0, sizeof(double) * 6 * N, h->st));
   activate(h);
@@ -1019,10 +1038,20 @@ int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
 int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "end_increment outside an increment");
   activate(h);
-  launch_commit(h->f, h->nsmax, h->dt, h->d_partials, h->st);
+  const int tex = h->ctrl.update_texture != 0, twn = (h->ctrl.update_twinning != 0 && h->f.twinf != nullptr);
+  if (tex) {
+    if (!h->f.de) {
+      CUDA_OK(h, cudaMalloc(&h->f.de, sizeof(double) * 6 * h->N));
+      CUDA_OK(h, cudaMemsetAsync(h->f.de, 0, sizeof(double) * 6 * h->N, h->st));
+    }
+    int rc = enqueue_rotation_field(h);
+    if (rc) return rc;
+  }
+  const double wapp[3] = {0.5 * (h->udot[7] - h->udot[5]), 0.5 * (h->udot[2] - h->udot[6]), 0.5 * (h->udot[3] - h->udot[1])};
+  launch_commit(h->f, h->nsmax, h->dt, wapp, tex, twn, h->d_partials, h->st);
   launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals + 16, h->st);
   if (h->nranks > 1) {
-    int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 10, kNcclDouble, kNcclSum, h->comm, h->st);
+    int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 10, kNcclDouble, kNcclSum, h->comm2 ? h->comm2 : h->comm, h->st);
     if (rc) return nccl_check(h, rc, "nccl allreduce (commit)");
   }
   double tot[11];
@@ -1030,6 +1059,27 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   CUDA_OK(h, cudaMemcpyAsync(h->h_macro, h->d_macro, sizeof(MacroDev), cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   CUDA_OK(h, cudaGetLastError());
+  const double Facc = tot[0] / h->Ntot;
+  long long nre = 0;
+  if (twn) {
+    const double Feff = (double)h->ntwinned / h->Ntot;
+    launch_twin_reorient(h->f, (Facc > 0.0) ? Feff / Facc : 0.0, h->d_partials, h->st);
+    launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals + 32, h->st);
+    if (h->nranks > 1) {
+      int rc = g_nccl.AllReduce(h->d_totals + 32, h->d_totals + 32, 1, kNcclDouble, kNcclSum, h->comm2 ? h->comm2 : h->comm, h->st);
+      if (rc) return nccl_check(h, rc, "nccl allreduce (PTR)");
+    }
+    double cnt = 0;
+    CUDA_OK(h, cudaMemcpyAsync(&cnt, h->d_totals + 32, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CUDA_OK(h, cudaStreamSynchronize(h->st));
+    nre = (long long)(cnt + 0.5);
+    h->ntwinned += nre;
+  }
+  if (tex || nre > 0) {   // orientations are now per voxel: the invariant tables go per voxel too (rebuilt at begin_increment)
+    int rc = switch_to_voxel_classes(h);
+    if (rc) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->st));
+  }
   MacroDev &m = *h->h_macro;
   // the pending macro correction belongs to an iteration that will not run
   for (int c = 0; c < 6; ++c) {
@@ -1047,6 +1097,7 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
     rep->err_stress = m.err_s; rep->err_strain = m.err_e;
     rep->converged = (m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
     for (int c = 0; c < 6; ++c) { rep->savg[c] = m.savg[c]; rep->emacro[c] = m.E[c]; rep->epavg[c] = tot[2 + c] / h->Ntot; }
+    rep->twin_acc = Facc; rep->twin_eff = (double)h->ntwinned / h->Ntot; rep->reoriented = nre;
   }
   return EVP_OK;
 }
@@ -1123,7 +1174,7 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   invalidate_green(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
   launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].out_inv, false, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, true, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_zfused(h->nz, 1, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

@@ -232,10 +232,12 @@ struct evp_solver {
   int nphases = 0, nsmax = 0;
   std::vector<PhaseData> ph;
   std::vector<int32_t> grain, phase;
-  std::vector<double> rot, sig, e, epsp, edotp, crss, gacc, twinf, de;
+  std::vector<double> rot, sig, e, epsp, edotp, crss, gacc, twinf, de, wrot;
+  std::vector<int32_t> twinned;
+  long long ntwinned = 0;
   double C0[36]{}, S0[36]{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
-  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100};
+  evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100, 0, 0};
   // loading
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};
@@ -441,6 +443,67 @@ void op_green(evp_solver *S) {
   for (int c = 0; c < 6; ++c) S->dEpend[c] = 0.0;
 }
 
+// Local rotation fluctuation of the compatible strain field e: for e^ = sym(u (x) xi),
+//   w^_ij = (e^_ik xi_k xi_j - e^_jk xi_k xi_i) / |xi|^2 = skew(u (x) xi);  zero at xi = 0 and on the Nyquist planes.
+// Output: axial components (w32, w13, w21) per voxel.
+void local_rotation(evp_solver *S, std::vector<double> &w) {
+  const int nx = S->nx, ny = S->ny, nz = S->nz, nxh = S->nxh;
+  const size_t N = S->N, NS = (size_t)nz * ny * nxh;
+  std::vector<cplx> sp(6 * NS);
+  for (int p = 0; p < 3; ++p)
+    fft3_forward_pair(S, &S->e[(2 * p) * N], &S->e[(2 * p + 1) * N], sp.data() + (2 * p) * NS, sp.data() + (2 * p + 1) * NS);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; ++z)
+    for (int y = 0; y < ny; ++y)
+      for (int kx = 0; kx < nxh; ++kx) {
+        const size_t idx = ((size_t)z * ny + y) * nxh + kx;
+        const int fx = freq_index(kx, nx), fy = freq_index(y, ny), fz = freq_index(z, nz);
+        cplx out[3] = {0.0, 0.0, 0.0};
+        const bool nyq = (nx % 2 == 0 && kx == nx / 2) || (ny % 2 == 0 && y == ny / 2) || (nz % 2 == 0 && z == nz / 2);
+        if (!(fx == 0 && fy == 0 && fz == 0) && !nyq) {
+          const double xi[3] = {(double)fx / (nx * S->g.dx), (double)fy / (ny * S->g.dy), (double)fz / (nz * S->g.dz)};
+          const double x2 = xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2];
+          cplx E[3][3];
+          for (int c = 0; c < 6; ++c) { E[kI[c]][kJ[c]] = sp[c * NS + idx]; E[kJ[c]][kI[c]] = sp[c * NS + idx]; }
+          cplx t[3];
+          for (int i = 0; i < 3; ++i) t[i] = E[i][0] * xi[0] + E[i][1] * xi[1] + E[i][2] * xi[2];
+          out[0] = (t[2] * xi[1] - t[1] * xi[2]) / x2;   // w32
+          out[1] = (t[0] * xi[2] - t[2] * xi[0]) / x2;   // w13
+          out[2] = (t[1] * xi[0] - t[0] * xi[1]) / x2;   // w21
+        }
+        for (int c = 0; c < 3; ++c) sp[c * NS + idx] = out[c];
+        sp[3 * NS + idx] = 0.0;
+      }
+  w.assign(4 * N, 0.0);
+  fft3_inverse_pair(S, sp.data(), sp.data() + NS, &w[0], &w[N]);
+  fft3_inverse_pair(S, sp.data() + 2 * NS, sp.data() + 3 * NS, &w[2 * N], &w[3 * N]);
+  w.resize(3 * N);
+}
+
+// R <- exp([w]x) R  (Rodrigues), w = axial vector (w32, w13, w21)
+void rotate_lattice(double *R, const double w[3]) {
+  const double th = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  double a, b;   // exp = I + a K + b K^2
+  if (th < 1e-8) { a = 1.0 - th * th / 6.0; b = 0.5 - th * th / 24.0; }
+  else { a = std::sin(th) / th; b = (1.0 - std::cos(th)) / (th * th); }
+  const double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double K2[9], Q[9], Rn[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += K[3 * i + k] * K[3 * k + j];
+      K2[3 * i + j] = s;
+    }
+  for (int k = 0; k < 9; ++k) Q[k] = ((k % 4 == 0) ? 1.0 : 0.0) + a * K[k] + b * K2[k];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += Q[3 * i + k] * R[3 * k + j];
+      Rn[3 * i + j] = s;
+    }
+  for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+}
+
 // plastic strain rate (Mandel, sample frame) and its stress derivative at stress s6 (Mandel)
 struct VoxelFrame {
   double Ssample[36];
@@ -607,7 +670,8 @@ size_t field_comps(const evp_solver *S, int f) {
     case EVP_FIELD_PLASTIC_RATE: case EVP_FIELD_STRAIN_INCR: return 6;
     case EVP_FIELD_CRSS: case EVP_FIELD_TWIN_FRACTION: return (size_t)S->nsmax;
     case EVP_FIELD_ROTATION: return 9;
-    case EVP_FIELD_GRAIN: case EVP_FIELD_PHASE: case EVP_FIELD_GAMMA_ACC: return 1;
+    case EVP_FIELD_GRAIN: case EVP_FIELD_PHASE: case EVP_FIELD_GAMMA_ACC: case EVP_FIELD_TWINNED: return 1;
+    case EVP_FIELD_LOCAL_ROTATION: return 3;
     default: return 0;
   }
 }
@@ -649,6 +713,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   S->epsp.assign(6 * N, 0.0); S->edotp.assign(6 * N, 0.0); S->de.assign(6 * N, 0.0);
   S->crss.assign((size_t)std::max(S->nsmax, 1) * N, 1.0); S->gacc.assign(N, 0.0);
   S->twinf.assign((size_t)std::max(S->nsmax, 1) * N, 0.0);
+  S->wrot.assign(3 * N, 0.0); S->twinned.assign(N, 0);
   S->px = FftPlan(S->nx); S->py = FftPlan(S->ny); S->pz = FftPlan(S->nz);
   *out = S;
   return EVP_OK;
@@ -681,6 +746,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   std::fill(h->epsp.begin(), h->epsp.end(), 0.0); std::fill(h->edotp.begin(), h->edotp.end(), 0.0);
   std::fill(h->gacc.begin(), h->gacc.end(), 0.0); std::fill(h->twinf.begin(), h->twinf.end(), 0.0);
   std::fill(h->de.begin(), h->de.end(), 0.0);
+  std::fill(h->wrot.begin(), h->wrot.end(), 0.0); std::fill(h->twinned.begin(), h->twinned.end(), 0); h->ntwinned = 0;
   for (size_t v = 0; v < N; ++v) {
     const PhaseData &pd = h->ph[h->phase[v]];
     for (int s = 0; s < h->nsmax; ++s)
@@ -800,21 +866,28 @@ int evp_equilibrium_iters(evp_handle h, int32_t n, evp_iter_report *last) {
 int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (!h || !h->in_incr) return fail(h, EVP_ERR_STATE, "end_increment outside an increment");
   const size_t N = h->N;
-  double epsum[6] = {0, 0, 0, 0, 0, 0};
-#pragma omp parallel for schedule(static) reduction(+ : epsum[:6])
+  const bool tex = h->ctrl.update_texture != 0, twn = h->ctrl.update_twinning != 0;
+  std::vector<double> wnew;
+  if (tex) local_rotation(h, wnew);
+  double wapp[3] = {0.5 * (h->udot[3 * 2 + 1] - h->udot[3 * 1 + 2]), 0.5 * (h->udot[3 * 0 + 2] - h->udot[3 * 2 + 0]),
+                    0.5 * (h->udot[3 * 1 + 0] - h->udot[3 * 0 + 1])};
+  double epsum[6] = {0, 0, 0, 0, 0, 0}, fsum = 0;
+#pragma omp parallel for schedule(static) reduction(+ : epsum[:6], fsum)
   for (size_t v = 0; v < N; ++v) {
     const PhaseData &pd = h->ph[h->phase[v]];
     VoxelFrame F;
     voxel_frame(h, v, F);
-    double s6[6], edp[6] = {0, 0, 0, 0, 0, 0}, dg[EVP_MAX_SYS], dG = 0;
+    double s6[6], edp[6] = {0, 0, 0, 0, 0, 0}, dg[EVP_MAX_SYS], gdv[EVP_MAX_SYS], dG = 0, wpc[3] = {0, 0, 0};
     for (int c = 0; c < 6; ++c) s6[c] = kW[c] * h->sig[c * N + v];
     for (int s = 0; s < pd.in.nsys; ++s) {
       double tau = 0, gd, dgd;
       for (int c = 0; c < 6; ++c) tau += F.msample[s][c] * s6[c];
       slip_rate(pd.in, s, tau, h->crss[(size_t)s * N + v], gd, dgd);
       for (int c = 0; c < 6; ++c) edp[c] += gd * F.msample[s][c];
+      gdv[s] = gd;
       dg[s] = std::fabs(gd) * h->dt;
       dG += dg[s];
+      for (int k = 0; k < 3; ++k) wpc[k] += pd.alpha[s][k] * gd;   // plastic spin, crystal frame
     }
     for (int c = 0; c < 6; ++c) {
       h->edotp[c * N + v] = edp[c] / kW[c];
@@ -835,6 +908,56 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
       for (int s = 0; s < pd.in.nsys; ++s) h->crss[(size_t)s * N + v] += dtau[s];
       h->gacc[v] = G0 + dG;
     }
+    if (twn) {  // twin volume fractions: df = dgamma / S_tw
+      for (int s = 0; s < pd.in.nsys; ++s) {
+        const int m = pd.in.mode[s];
+        if (pd.in.twin[m] && pd.in.twin_shear[m] > 0) h->twinf[(size_t)s * N + v] += gdv[s] * h->dt / pd.in.twin_shear[m];
+        if (pd.in.twin[m]) fsum += h->twinf[(size_t)s * N + v];
+      }
+    }
+    if (tex) {  // lattice spin = applied spin + local (FFT) spin - plastic spin
+      double R[9], wps[3], dw[3];
+      for (int k = 0; k < 9; ++k) R[k] = h->rot[k * N + v];
+      for (int i = 0; i < 3; ++i) wps[i] = R[3 * i] * wpc[0] + R[3 * i + 1] * wpc[1] + R[3 * i + 2] * wpc[2];
+      for (int k = 0; k < 3; ++k) {
+        dw[k] = h->dt * wapp[k] + (wnew[k * N + v] - h->wrot[k * N + v]) - h->dt * wps[k];
+        h->wrot[k * N + v] = wnew[k * N + v];
+      }
+      rotate_lattice(R, dw);
+      for (int k = 0; k < 9; ++k) h->rot[k * N + v] = R[k];
+    }
+  }
+  // PTR: a voxel whose predominant twin system exceeds thr1 + thr2 * F_eff / F_acc takes the twin orientation
+  long long nre = 0;
+  const double Facc = fsum / (double)N, Feff = (double)h->ntwinned / (double)N;
+  if (twn) {
+#pragma omp parallel for schedule(static) reduction(+ : nre)
+    for (size_t v = 0; v < N; ++v) {
+      if (h->twinned[v]) continue;
+      const PhaseData &pd = h->ph[h->phase[v]];
+      const double thr = pd.in.twin_thr1 + ((Facc > 0) ? pd.in.twin_thr2 * Feff / Facc : 0.0);
+      int best = -1;
+      double fb = 0;
+      for (int s = 0; s < pd.in.nsys; ++s)
+        if (pd.in.twin[pd.in.mode[s]] && h->twinf[(size_t)s * N + v] > fb) { fb = h->twinf[(size_t)s * N + v]; best = s; }
+      if (best < 0 || !(fb > thr)) continue;
+      double n[3], nl = 0, R[9], Rn[9];
+      for (int k = 0; k < 3; ++k) nl += pd.in.n[best][k] * pd.in.n[best][k];
+      nl = std::sqrt(nl);
+      for (int k = 0; k < 3; ++k) n[k] = pd.in.n[best][k] / nl;
+      for (int k = 0; k < 9; ++k) R[k] = h->rot[k * N + v];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {  // R (2 n n^T - I)
+          double s = 0;
+          for (int k = 0; k < 3; ++k) s += R[3 * i + k] * (2.0 * n[k] * n[j] - (k == j ? 1.0 : 0.0));
+          Rn[3 * i + j] = s;
+        }
+      for (int k = 0; k < 9; ++k) h->rot[k * N + v] = Rn[k];
+      for (int s = 0; s < pd.in.nsys; ++s) h->twinf[(size_t)s * N + v] = 0.0;
+      h->twinned[v] = 1;
+      nre += 1;
+    }
+    h->ntwinned += nre;
   }
   // the pending macro correction belongs to an iteration that will not run: drop it, so that
   // the committed E is the mean of the committed strain field e
@@ -850,6 +973,7 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
     rep->err_stress = h->last_err_s; rep->err_strain = h->last_err_e;
     rep->converged = (h->last_err_s <= h->ctrl.tol_stress && h->last_err_e <= h->ctrl.tol_strain) ? 1 : 0;
     for (int c = 0; c < 6; ++c) { rep->savg[c] = h->savg[c]; rep->emacro[c] = h->E[c]; rep->epavg[c] = epsum[c] / (double)N; }
+    rep->twin_acc = Facc; rep->twin_eff = (double)h->ntwinned / (double)N; rep->reoriented = nre;
   }
   return EVP_OK;
 }
@@ -883,6 +1007,8 @@ static void *field_ptr(evp_solver *S, int f, size_t *elem) {
     case EVP_FIELD_GAMMA_ACC: return S->gacc.data();
     case EVP_FIELD_TWIN_FRACTION: return S->twinf.data();
     case EVP_FIELD_STRAIN_INCR: return S->de.data();
+    case EVP_FIELD_LOCAL_ROTATION: return S->wrot.data();
+    case EVP_FIELD_TWINNED: *elem = sizeof(int32_t); return S->twinned.data();
     case EVP_FIELD_GRAIN: *elem = sizeof(int32_t); return S->grain.data();
     case EVP_FIELD_PHASE: *elem = sizeof(int32_t); return S->phase.data();
     default: return nullptr;

@@ -8,7 +8,12 @@ from lapx_b200 import api, microstructure as ms
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_phase(host, hcp: bool):
+def golden_phase(host, hcp: bool, kind: int = 0):
+    if kind == 2:
+        import sys
+        sys.path.insert(0, GOLDEN)
+        from common_golden import twin_phase
+        return twin_phase(host)
     if hcp:
         return ms.hcp_phase(host, with_twin=1, nrate=10.0,
                             voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
@@ -22,12 +27,14 @@ def load_golden(name):
 def solver_from_golden(lib, host, g, c0="golden"):
     """Create a Solver on `lib` with the inputs stored in golden file `g` (phase tables from `host`)."""
     grid = tuple(int(v) for v in g["grid"])
-    ph = golden_phase(host, bool(int(g["hcp"])))
+    ph = golden_phase(host, bool(int(g["hcp"])), int(g["phase_kind"]) if "phase_kind" in g.files else 0)
     s = api.Solver(lib, grid, [ph])
     rot9 = ms.expand_rotations(g["grain"], g["grain_rot"])
     s.set_microstructure(g["grain"], None, rot9)
     s.set_reference_medium(g["c0_voigt"] if c0 == "golden" else None)
-    s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, itmin=1, tol_newton=1e-9, newton_itmax=100)
+    s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, itmin=1, tol_newton=1e-9, newton_itmax=100,
+                  update_texture=int(g["texture"]) if "texture" in g.files else 0,
+                  update_twinning=int(g["twinning"]) if "twinning" in g.files else 0)
     s.set_loading(api.Loading(g["iudot"], g["udot"], g["iscau"], g["scau"]))
     return s
 

@@ -20,6 +20,7 @@ import scipy.fft as sfft
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lapx_b200 import api, microstructure as ms  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 VM = np.array([[0, 5, 4], [5, 1, 3], [4, 3, 2]])
 PAIRS = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
@@ -99,7 +100,7 @@ class NumpyEVP:
         self.shape = grain.shape                      # (nz, ny, nx)
         nz, ny, nx = self.shape
         self.N = grain.size
-        R = grain_rot[grain.reshape(-1)]              # (N,3,3) crystal -> sample
+        R = grain_rot[grain.reshape(-1)].copy()       # (N,3,3) crystal -> sample
         self.R = R
         ns = phase.nsys
         self.ns = ns
@@ -107,15 +108,15 @@ class NumpyEVP:
         n = np.array([[phase.n[s][k] for k in range(3)] for s in range(ns)])
         b /= np.linalg.norm(b, axis=1, keepdims=True)
         n /= np.linalg.norm(n, axis=1, keepdims=True)
-        mc = 0.5 * (np.einsum("si,sj->sij", b, n) + np.einsum("si,sj->sij", n, b))
-        self.m = np.einsum("via,sab,vjb->vsij", R, mc, R)           # (N,ns,3,3) sample frame
-        self.m6 = sym_to_m6(self.m)                                 # (N,ns,6)
-        Cc = voigt_to_t4(np.array(list(phase.c_voigt)))
+        self.bc, self.nc = b, n
+        self.mc = 0.5 * (np.einsum("si,sj->sij", b, n) + np.einsum("si,sj->sij", n, b))
+        self.qc = 0.5 * (np.einsum("si,sj->sij", b, n) - np.einsum("si,sj->sij", n, b))   # skew part, crystal frame
+        self.Cc = voigt_to_t4(np.array(list(phase.c_voigt)))
+        Cc = self.Cc
         # rotate per grain, then gather
         Cg = np.einsum("gia,gjb,gkc,gld,abcd->gijkl", grain_rot, grain_rot, grain_rot, grain_rot, Cc)
         Cm6 = np.einsum("aij,gijkl,bkl->gab", B6, Cg, B6)
-        Sm6 = np.linalg.inv(Cm6)
-        self.S6 = Sm6[grain.reshape(-1)]                            # (N,6,6)
+        self.rebuild_from_R()
         if c0_voigt is None:
             counts = np.bincount(grain.reshape(-1), minlength=len(grain_rot)).astype(float)
             C0m = np.einsum("g,gab->ab", counts, Cm6) / counts.sum()
@@ -142,7 +143,44 @@ class NumpyEVP:
         self.dEpend = np.zeros(6)
         self.Edot_prev = np.zeros(6)
         self.tol_newton, self.newton_itmax = 1e-9, 100
+        self.update_texture = self.update_twinning = False
+        self.wrot = np.zeros((self.N, 3))
+        self.twinf = np.zeros((self.N, ns))
+        self.twinned = np.zeros(self.N, bool)
+        self.tshear = np.array([phase.twin_shear[m] for m in mode])
         self.W = np.array([1, 1, 1, np.sqrt(2), np.sqrt(2), np.sqrt(2)])
+
+    def rebuild_from_R(self):
+        """Orientation-dependent quantities of every voxel from its current rotation."""
+        R = self.R
+        self.m = np.einsum("via,sab,vjb->vsij", R, self.mc, R)      # (N,ns,3,3) sample frame
+        self.m6 = sym_to_m6(self.m)                                 # (N,ns,6)
+        Cv = np.einsum("via,vjb,vkc,vld,abcd->vijkl", R, R, R, R, self.Cc)
+        self.S6 = np.linalg.inv(np.einsum("aij,vijkl,bkl->vab", B6, Cv, B6))   # (N,6,6)
+
+    def local_rotation(self):
+        """Axial (w32,w13,w21) of skew(grad u) of the compatible strain field e; zero at xi=0 and Nyquist."""
+        nz, ny, nx = self.shape
+        eh = sfft.rfftn(m6_to_sym(self.e).reshape(nz, ny, nx, 3, 3), axes=(0, 1, 2))
+        fz = sfft.fftfreq(nz) * nz
+        fy = sfft.fftfreq(ny) * ny
+        fx = sfft.rfftfreq(nx) * nx
+        xi = np.stack(np.meshgrid(fz / nz, fy / ny, fx / nx, indexing="ij")[::-1], axis=-1)
+        x2 = (xi ** 2).sum(-1)
+        x2[0, 0, 0] = 1.0
+        t = np.einsum("...ik,...k->...i", eh, xi)
+        wh = (np.einsum("...i,...j->...ij", t, xi) - np.einsum("...j,...i->...ij", t, xi)) / x2[..., None, None]
+        nyq = np.zeros((nz, ny, nx // 2 + 1), bool)
+        if nz % 2 == 0:
+            nyq[nz // 2, :, :] = True
+        if ny % 2 == 0:
+            nyq[:, ny // 2, :] = True
+        if nx % 2 == 0:
+            nyq[:, :, nx // 2] = True
+        wh[nyq] = 0.0
+        wh[0, 0, 0] = 0.0
+        w = sfft.irfftn(wh, s=(nz, ny, nx), axes=(0, 1, 2)).reshape(self.N, 3, 3)
+        return np.stack([w[:, 2, 1], w[:, 0, 2], w[:, 1, 0]], axis=1)
 
     # ---- loading ----
     def set_loading(self, ld: api.Loading):
@@ -269,6 +307,44 @@ class NumpyEVP:
                 dtau = np.where(dG > 0, dv * hs / dG, 0.0)
             self.crss[:, s] = self.crss[:, s] + dtau
         self.gacc = self.gacc + dG
+        nre = 0
+        if self.update_twinning:
+            tw = self.twin & (self.tshear > 0)
+            self.twinf[:, tw] += gd[:, tw] * self.dt / self.tshear[tw]
+            Facc = self.twinf[:, self.twin].sum() / self.N
+            Feff = self.twinned.sum() / self.N
+        if self.update_texture:
+            wnew = self.local_rotation()
+            W = 0.5 * (self.udot - self.udot.T)
+            wapp = np.array([W[2, 1], W[0, 2], W[1, 0]])
+            qs = np.einsum("vs,sij->vij", gd, self.qc)                    # plastic spin, crystal frame
+            wpc = np.stack([qs[:, 2, 1], qs[:, 0, 2], qs[:, 1, 0]], axis=1)
+            wps = np.einsum("vij,vj->vi", self.R, wpc)
+            dw = self.dt * wapp[None, :] + (wnew - self.wrot) - self.dt * wps
+            self.wrot = wnew
+            th = np.linalg.norm(dw, axis=1)
+            K = np.zeros((self.N, 3, 3))
+            K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -dw[:, 2], dw[:, 1], dw[:, 2], -dw[:, 0], -dw[:, 1], dw[:, 0]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                a = np.where(th < 1e-8, 1 - th ** 2 / 6, np.sin(th) / th)
+                b = np.where(th < 1e-8, 0.5 - th ** 2 / 24, (1 - np.cos(th)) / th ** 2)
+            Q = np.eye(3)[None] + a[:, None, None] * K + b[:, None, None] * (K @ K)
+            self.R = Q @ self.R
+        if self.update_twinning:
+            thr = self.phase.twin_thr1 + (self.phase.twin_thr2 * Feff / Facc if Facc > 0 else 0.0)
+            ftw = np.where(self.twin[None, :], self.twinf, -1.0)
+            best = ftw.argmax(axis=1)
+            fb = ftw.max(axis=1)
+            hit = (~self.twinned) & (fb > thr) & (fb > 0)
+            for v in np.where(hit)[0]:
+                nvec = self.nc[best[v]]
+                self.R[v] = self.R[v] @ (2 * np.outer(nvec, nvec) - np.eye(3))
+                self.twinf[v] = 0.0
+                self.twinned[v] = True
+            nre = int(hit.sum())
+            self.last_twin = (Facc, self.twinned.sum() / self.N, nre)
+        if self.update_texture or nre:
+            self.rebuild_from_R()
         self.E = self.E - self.dEpend
         self.dEpend[:] = 0.0
         self.Edot_prev = (self.E - self.Et) / self.dt
@@ -278,12 +354,14 @@ class NumpyEVP:
         return np.ascontiguousarray((v6 / self.W).T).reshape((6,) + self.shape)
 
 
-def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs, phase=None, hcp=False, slim=False):
+def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs, phase=None, hcp=False, slim=False, texture=False,
+              twinning=False, phase_kind=0):
     nx, ny, nz = grid
     ids, grot = ms.voronoi(lib, grid, ngrains, seed)
     if phase is None:
         phase = ms.fcc_phase(lib, gamma0=1.0, nrate=10.0, tau0=16.0, tau1=10.0, theta0=200.0, theta1=10.0)
     S = NumpyEVP(phase, ids, grot)
+    S.update_texture, S.update_twinning = texture, twinning
     S.set_loading(loading)
     reports = []
     fields = {}
@@ -304,6 +382,11 @@ def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs,
         fields[f"e_end_inc{inc}"] = S.field(S.e)
         fields[f"epsp_end_inc{inc}"] = S.field(S.epsp)
         fields[f"crss_end_inc{inc}"] = np.ascontiguousarray(S.crss.T).reshape((S.ns, nz, ny, nx))
+        if texture or twinning:
+            fields[f"rot_end_inc{inc}"] = np.ascontiguousarray(S.R.reshape(S.N, 9).T).reshape((9, nz, ny, nx))
+            fields[f"twinned_end_inc{inc}"] = S.twinned.reshape(nz, ny, nx).astype(np.int32)
+            if twinning:
+                print("   inc", inc, "twin F_acc, F_eff, reoriented:", S.last_twin)
     if slim:  # keep the fixture small: final stress and strain only
         last = nincs - 1
         fields = {k: v for k, v in fields.items() if k in (f"sig_end_inc{last}", f"e_end_inc{last}")}
@@ -313,7 +396,7 @@ def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs,
         out, grid=np.array(grid), ngrains=ngrains, seed=seed, grain=ids, grain_rot=grot, c0_voigt=c0v,
         iudot=np.asarray(loading.iudot), udot=np.asarray(loading.udot), iscau=np.asarray(loading.iscau),
         scau=np.asarray(loading.scau), dt=dt, iters_per_inc=iters_per_inc, nincs=nincs,
-        reports=np.array(reports), hcp=int(hcp), **fields)
+        reports=np.array(reports), hcp=int(hcp), texture=int(texture), twinning=int(twinning), phase_kind=phase_kind, **fields)
     print("wrote", out, os.path.getsize(out), "bytes; last report", reports[-1][:5])
 
 
@@ -326,6 +409,12 @@ def main():
     hcp = ms.hcp_phase(lib, with_twin=1, nrate=10.0,
                        voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
     make_case(lib, "hcp8_compression", (8, 8, 8), 5, 7, api.Loading.strain_rate(-D), 2e-4, 10, 2, phase=hcp, hcp=True)
+    make_case(lib, "fcc8_texture", (8, 8, 8), 6, 2, api.Loading.strain_rate(D + np.array([[0, 0.3, 0], [-0.3, 0, 0], [0, 0, 0]])), 5e-4, 8, 3,
+              texture=True)
+    # HCP with easy tensile twinning and low PTR thresholds so that voxels reorient within a few increments
+    from common_golden import twin_phase
+    make_case(lib, "hcp8_twin_texture", (8, 8, 8), 5, 11, api.Loading.strain_rate(D), 1e-3, 8, 4, phase=twin_phase(lib), hcp=True,
+              texture=True, twinning=True, phase_kind=2)
 
 
 if __name__ == "__main__":

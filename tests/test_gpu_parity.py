@@ -12,7 +12,7 @@ from lapx_b200 import api, microstructure as ms
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-8
-GPU_GOLDEN = ["fcc8_strain", "hcp8_compression", "fcc_16x8x32_tension"]
+GPU_GOLDEN = ["fcc8_strain", "hcp8_compression", "fcc_16x8x32_tension", "fcc8_texture", "hcp8_twin_texture"]
 
 
 def test_backend_is_cuda(product_lib):
@@ -44,6 +44,8 @@ def test_gpu_matches_numpy_golden(name, per_voxel, product_lib, monkeypatch):
             seen[f"e_end_inc{inc}"] = s.get_field(api.FIELD_STRAIN)
             seen[f"epsp_end_inc{inc}"] = s.get_field(api.FIELD_PLASTIC_STRAIN)
             seen[f"crss_end_inc{inc}"] = s.get_field(api.FIELD_CRSS)
+            seen[f"rot_end_inc{inc}"] = s.get_field(api.FIELD_ROTATION)          # lattice rotation / PTR reorientation
+            seen[f"twinned_end_inc{inc}"] = s.get_field(api.FIELD_TWINNED)[0]    # integer flags: bit exact
 
     rows = run_golden_schedule(s, g, hook)
     ref = g["reports"]

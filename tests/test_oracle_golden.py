@@ -6,7 +6,7 @@ import pytest
 from common import load_golden, rel_err, run_golden_schedule, solver_from_golden
 from lapx_b200 import api
 
-CASES = ["fcc8_strain", "fcc_12x10x8_tension", "hcp8_compression", "fcc_16x8x32_tension"]
+CASES = ["fcc8_strain", "fcc_12x10x8_tension", "hcp8_compression", "fcc_16x8x32_tension", "fcc8_texture", "hcp8_twin_texture"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -26,6 +26,8 @@ def test_oracle_matches_numpy_golden(name, oracle_lib, product_lib):
             seen[f"e_end_inc{inc}"] = s.get_field(api.FIELD_STRAIN)
             seen[f"epsp_end_inc{inc}"] = s.get_field(api.FIELD_PLASTIC_STRAIN)
             seen[f"crss_end_inc{inc}"] = s.get_field(api.FIELD_CRSS)
+            seen[f"rot_end_inc{inc}"] = s.get_field(api.FIELD_ROTATION)
+            seen[f"twinned_end_inc{inc}"] = s.get_field(api.FIELD_TWINNED)[0]
 
     rows = run_golden_schedule(s, g, hook)
     ref = g["reports"]
