@@ -61,6 +61,16 @@ def build_product(force=False, verbose=False):
     return OUT
 
 
+def build_driver(force=False):
+    """Host driver executable (C++17) linked against the product library."""
+    src = os.path.join(CSRC, "driver", "evpfft_main.cpp")
+    out = os.path.join(HERE, "evpfft_driver")
+    if force or needs_build(out, [src, OUT, os.path.join(ROOT, "include", "evpfft.h")]):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++17", "-o", out, src, "-L", HERE, "-levpfft_b200", "-Wl,-rpath,$ORIGIN"], check=True)
+    return out
+
+
 def build_oracle(force=False):
     out = os.path.join(ROOT, "oracle", "libevp_oracle.so")
     deps = [os.path.join(ROOT, "oracle", "evp_oracle.cpp"), os.path.join(ROOT, "include", "evpfft.h")]
@@ -71,4 +81,5 @@ def build_oracle(force=False):
 
 if __name__ == "__main__":
     print(build_product(force="--force" in sys.argv, verbose=True))
+    print(build_driver(force="--force" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))
