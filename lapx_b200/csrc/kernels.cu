@@ -725,12 +725,17 @@ __global__ void __launch_bounds__(256) k_reduce1(const double *__restrict__ part
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(32) k_reduce2(const double *__restrict__ scratch, int nb, double *__restrict__ totals) {
-  const int k = threadIdx.x;
-  if (k >= 11) return;
+// one warp per quantity: lanes stride over the stage-1 partials, fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(352) k_reduce2(const double *__restrict__ scratch, int nb, double *__restrict__ totals) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double acc = 0.0;
-  for (int b = 0; b < nb; ++b) acc = (k < 10) ? acc + scratch[(long long)b * 16 + k] : fmax(acc, scratch[(long long)b * 16 + k]);
-  totals[k] = acc;
+  for (int b = lane; b < nb; b += 32) acc = (k < 10) ? acc + scratch[(long long)b * 16 + k] : fmax(acc, scratch[(long long)b * 16 + k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+    acc = (k < 10) ? acc + other : fmax(acc, other);
+  }
+  if (lane == 0) totals[k] = acc;
 }
 
 // rows a6 (normalisation) + a7 (macro strain correction) on the device.
@@ -1096,7 +1101,7 @@ void launch_reduce(const double *partials, long long N, double *scratch, double 
   const long long nw = num_warps(N);
   const int nb = (int)((nw < kRedBlocks) ? nw : kRedBlocks);
   k_reduce1<<<nb, 256, 0, st>>>(partials, nw, scratch);
-  k_reduce2<<<1, 32, 0, st>>>(scratch, nb, totals);
+  k_reduce2<<<1, 352, 0, st>>>(scratch, nb, totals);
 }
 void launch_macro(const double *totals, MacroDev *macro, double ntot, cudaStream_t st) { k_macro<<<1, 32, 0, st>>>(totals, macro, ntot); }
 void launch_fill(double *p, long long n, double v, cudaStream_t st) { k_fill<<<592, 256, 0, st>>>(p, n, v); }
