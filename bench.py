@@ -318,10 +318,10 @@ def main():
         "e2e": {"value": N * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 42 * 8, "d2h_bytes_per_step": 616,
                 "what": "evp_set_loading + evp_equilibrium_iter per step through the C ABI: BC upload, report download, host sync; "
                         "fields stay device resident by design (one-off transfer cost under config.setup)"},
-        "gpu_launches": 9 * args.steps,
+        "gpu_launches": ((4 if world > 1 else 1) * 5 + 4) * args.steps,   # per iteration: 5 kernels per z-chunk + z pass + 2 reductions + macro
         "clocks": clk,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(lib, args.workload)
     print(json.dumps(out))
 
