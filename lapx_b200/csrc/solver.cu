@@ -704,7 +704,14 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
     CK(cudaEventCreate(&S->ev_it0));
     CK(cudaEventCreate(&S->ev_it1));
     if (nranks > 1) {
-      CK(cudaStreamCreateWithFlags(&S->stc, cudaStreamNonBlocking));
+      {
+        // EVP_COMM_PRIO: 0 = same priority as the compute stream (default), 1 = lower, -1 = higher
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int mode = getenv("EVP_COMM_PRIO") ? atoi(getenv("EVP_COMM_PRIO")) : 0;
+        const int pr = (mode > 0) ? lo : (mode < 0 ? hi : 0);
+        CK(cudaStreamCreateWithPriority(&S->stc, cudaStreamNonBlocking, pr));
+      }
       CK(cudaEventCreateWithFlags(&S->ev_k4, cudaEventDisableTiming));
     }
   }

@@ -265,3 +265,56 @@ def test_error_behaviour_matches_oracle(product_lib):
     assert ei.value.code == -2
     with pytest.raises(api.EvpError):
         s.op_green()
+
+
+def _two_phase_solvers(product_lib, oracle_lib, grid, nrate_a=10.0, nrate_b=10.0):
+    """FCC + HCP phases in one polycrystal (generic kernel variant: runtime system count, per-voxel phase tables)."""
+    pa = ms.fcc_phase(product_lib, nrate=nrate_a, tau0=16.0, tau1=10.0, theta0=200.0, theta1=10.0)
+    pb = ms.hcp_phase(product_lib, with_twin=1, nrate=nrate_b,
+                      voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
+    ids, grot = ms.voronoi(product_lib, grid, 14, 9)
+    phase = (ids % 2).astype(np.int32)            # alternate grains between the two phases
+    sols = []
+    for lib in (product_lib, oracle_lib):
+        s = api.Solver(lib, grid, [pa, pb])
+        s.set_microstructure(ids, phase, ms.expand_rotations(ids, grot))
+        s.set_reference_medium(None)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.uniaxial_tension(1.0))
+        sols.append(s)
+    return sols, phase
+
+
+@pytest.mark.parametrize("nrates", [(10.0, 10.0), (7.5, 12.0)])
+def test_two_phase_and_noninteger_exponent_vs_oracle(nrates, product_lib, oracle_lib):
+    (gpu, orc), phase = _two_phase_solvers(product_lib, oracle_lib, (16, 16, 32), *nrates)
+    assert gpu.nsys_max == 24
+    for inc in range(2):
+        gpu.begin_increment(2e-4)
+        orc.begin_increment(2e-4)
+        for it in range(6):
+            rg, ro = gpu.equilibrium_iter(), orc.equilibrium_iter()
+            assert rg.newton_max == ro.newton_max
+            assert rel_err(rg.savg[:], ro.savg[:]) < TOL
+        gpu.end_increment()
+        orc.end_increment()
+    for f in (api.FIELD_STRESS, api.FIELD_STRAIN, api.FIELD_PLASTIC_STRAIN, api.FIELD_CRSS):
+        assert rel_err(gpu.get_field(f), orc.get_field(f)) < TOL, f
+    assert np.array_equal(gpu.get_field(api.FIELD_PHASE)[0], phase)      # phase indexing bit exact
+
+
+def test_elastic_only_phase(product_lib, oracle_lib):
+    """nsys = 0 (no slip systems): the local problem is linear, one Newton update + the stopping check."""
+    ph = ms.fcc_phase(product_lib)
+    ph.nsys = 0
+    sols = []
+    for lib in (product_lib, oracle_lib):
+        s, ids, grot = make_polycrystal(lib, product_lib, (16, 16, 16), 8, seed=2, phase=ph)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.strain_rate(np.diag([-0.5, -0.5, 1.0])))
+        s.begin_increment(2e-4)
+        for _ in range(8):
+            r = s.equilibrium_iter()
+        sols.append((s.get_field(api.FIELD_STRESS), r))
+    assert rel_err(sols[0][0], sols[1][0]) < TOL
+    assert sols[0][1].newton_max == sols[1][1].newton_max <= 2
