@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--workload", default="fcc", choices=["fcc", "hcp"])
     ap.add_argument("--grid", default=None, help="override, e.g. 128x128x128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cufft", action="store_true", help="also time cuFFT (torch.fft) on the same 6 fields, as a comparison only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -321,6 +322,23 @@ def main():
         "gpu_launches": ((4 if world > 1 else 1) * 5 + 4) * args.steps,   # per iteration: 5 kernels per z-chunk + z pass + 2 reductions + macro
         "clocks": clk,
     }
+    if args.cufft and world == 1:
+        # comparison only (BASELINE.json north_star: "cuFFT timed only as a comparison"): 6 real fields, rfftn + irfftn
+        x = torch.randn((6,) + tuple(reversed(grid)), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            y = torch.fft.irfftn(torch.fft.rfftn(x, dim=(1, 2, 3)), s=x.shape[1:], dim=(1, 2, 3))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            y = torch.fft.irfftn(torch.fft.rfftn(x, dim=(1, 2, 3)), s=x.shape[1:], dim=(1, 2, 3))
+        e1.record()
+        torch.cuda.synchronize()
+        ours = sum(k["ms"] for k in kern if k["name"] != "constitutive")
+        out["cufft_compare"] = {"cufft_rfftn_plus_irfftn_6_fields_ms": round(e0.elapsed_time(e1) / 5, 4),
+                                "ours_fft_chain_ms": round(ours, 4),
+                                "note": "ours includes the Green operator and the strain update; cuFFT figure is transforms only, out of place"}
+        del x, y
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(lib, args.workload)
     print(json.dumps(out))

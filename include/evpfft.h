@@ -190,6 +190,14 @@ int  evp_get_field(evp_handle h, evp_field f, void *host, size_t bytes);
 int  evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes);
 int  evp_get_macro(evp_handle h, double emacro[6], double savg[6]);
 
+/* ---- checkpoint / restart ------------------------------------------- */
+/* One raw binary file per rank: header (magic "EVPCKPT1", grid, slab, nsys_max), macroscopic state, then the state
+ * fields in the ABI layout: stress, strain, plastic strain, CRSS, rotation, accumulated shear, twin fractions,
+ * local rotation, grain, phase, twin flags.  evp_load_state needs a handle created with the same grid / phases /
+ * decomposition and with the reference medium and loading already set.                                            */
+int  evp_save_state(evp_handle h, const char *path);
+int  evp_load_state(evp_handle h, const char *path);
+
 /* ---- test / measurement hooks (same in both back ends) ------------------------------- */
 /* Half spectrum of the forward 3-D r2c FFT (row a1) of stress component `comp`:
  * out[(z*ny + y)*(nx/2+1) + kx] as interleaved (re,im).  Single-rank handles only.        */

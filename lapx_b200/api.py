@@ -97,7 +97,7 @@ ABI_SYMBOLS_COMMON = [
     "evp_equilibrium_iter", "evp_op_green", "evp_op_constitutive", "evp_end_increment",
     "evp_step", "evp_equilibrium_iters", "evp_field_components", "evp_get_field",
     "evp_set_field", "evp_get_macro", "evp_debug_spectrum", "evp_stream",
-    "evp_set_profiling", "evp_last_kernel_ms", "evp_transport",
+    "evp_set_profiling", "evp_last_kernel_ms", "evp_transport", "evp_save_state", "evp_load_state",
 ]
 ABI_SYMBOLS_PRODUCT_ONLY = ["evp_phase_fcc", "evp_phase_hcp", "evp_voronoi", "evp_nccl_unique_id"]
 
@@ -136,6 +136,8 @@ def _proto(lib):
         "evp_set_profiling": ([H, C.c_int32], C.c_int),
         "evp_last_kernel_ms": ([H, C.c_void_p], C.c_int),
         "evp_transport": ([H], C.c_int),
+        "evp_save_state": ([H, C.c_char_p], C.c_int),
+        "evp_load_state": ([H, C.c_char_p], C.c_int),
         "evp_phase_fcc": ([P(Phase)] + [C.c_double] * 9, C.c_int),
         "evp_phase_hcp": ([P(Phase), C.c_double, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                            C.c_void_p, C.c_void_p], C.c_int),
@@ -357,6 +359,12 @@ class Solver:
         out = np.empty((self.nz, self.ny, self.nx // 2 + 1), dtype=np.complex128)
         self._check(self.lib.evp_debug_spectrum(self.h, comp, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def save_state(self, path: str):
+        self._check(self.lib.evp_save_state(self.h, str(path).encode()))
+
+    def load_state(self, path: str):
+        self._check(self.lib.evp_load_state(self.h, str(path).encode()))
 
     def set_profiling(self, on: bool):
         self._check(self.lib.evp_set_profiling(self.h, int(on)))

@@ -1174,6 +1174,85 @@ int evp_get_macro(evp_handle h, double emacro[6], double savg[6]) {
   return EVP_OK;
 }
 
+
+struct CkptHeader {
+  char magic[8];
+  int32_t nx, ny, nz, z0, nzl, nsmax, nranks, rank;
+  double Et[6], Edot_prev[6];
+  int64_t ntwinned;
+};
+
+static int ckpt_io(evp_handle h, std::FILE *f, bool write) {
+  const size_t N = (size_t)h->N, ns = (size_t)std::max(h->nsmax, 1);
+  struct Item { void *p; size_t bytes; };
+  const Item items[] = {{h->f.sig, 6 * N * 8}, {h->f.e, 6 * N * 8}, {h->f.epsp, 6 * N * 8}, {h->f.crss, ns * N * 8}, {h->f.rot, 9 * N * 8},
+                        {h->f.gacc, N * 8}, {h->f.twinf, ns * N * 8}, {h->f.wrot, 3 * N * 8}, {h->f.grain, N * 4}, {h->f.phase, N * 4},
+                        {h->f.twinned, N * 4}};
+  const size_t kBuf = (size_t)64 << 20;
+  std::vector<char> buf(kBuf);
+  for (const Item &it : items) {
+    for (size_t off = 0; off < it.bytes; off += kBuf) {
+      const size_t nb = std::min(kBuf, it.bytes - off);
+      if (write) {
+        if (it.p) { CUDA_OK(h, cudaMemcpy(buf.data(), (char *)it.p + off, nb, cudaMemcpyDeviceToHost)); }
+        else std::memset(buf.data(), 0, nb);   // optional field not allocated (twin fractions without twin modes)
+        if (std::fwrite(buf.data(), 1, nb, f) != nb) return fail(h, EVP_ERR_ARG, "short write");
+      } else {
+        if (std::fread(buf.data(), 1, nb, f) != nb) return fail(h, EVP_ERR_ARG, "short read");
+        if (it.p) CUDA_OK(h, cudaMemcpy((char *)it.p + off, buf.data(), nb, cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  return EVP_OK;
+}
+
+int evp_save_state(evp_handle h, const char *path) {
+  if (!h || !path) return EVP_ERR_ARG;
+  if (h->in_incr) return fail(h, EVP_ERR_STATE, "save_state inside an increment");
+  cudaSetDevice(h->device);
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  std::FILE *f = std::fopen(path, "wb");
+  if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot write ") + path);
+  CkptHeader hd{};
+  std::memcpy(hd.magic, "EVPCKPT1", 8);
+  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.z0 = h->z0; hd.nzl = h->nzl; hd.nsmax = h->nsmax; hd.nranks = h->nranks; hd.rank = h->rank;
+  for (int c = 0; c < 6; ++c) { hd.Et[c] = h->Et[c]; hd.Edot_prev[c] = h->Edot_prev[c]; }
+  hd.ntwinned = h->ntwinned;
+  int rc = (std::fwrite(&hd, sizeof(hd), 1, f) == 1) ? EVP_OK : fail(h, EVP_ERR_ARG, "short write");
+  if (rc == EVP_OK) rc = ckpt_io(h, f, true);
+  std::fclose(f);
+  return rc;
+}
+
+int evp_load_state(evp_handle h, const char *path) {
+  if (!h || !path) return EVP_ERR_ARG;
+  if (h->in_incr) return fail(h, EVP_ERR_STATE, "load_state inside an increment");
+  activate(h);
+  invalidate_green(h);
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  std::FILE *f = std::fopen(path, "rb");
+  if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot read ") + path);
+  CkptHeader hd{};
+  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT1", 8) == 0;
+  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nzl || hd.z0 != h->z0 || hd.nsmax != h->nsmax)) ok = false;
+  if (!ok) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint does not match this handle"); }
+  int rc = ckpt_io(h, f, false);
+  std::fclose(f);
+  if (rc) return rc;
+  MacroDev &m = *h->h_macro;
+  for (int c = 0; c < 6; ++c) {
+    h->Et[c] = hd.Et[c]; h->Edot_prev[c] = hd.Edot_prev[c];
+    m.E[c] = m.Et[c] = hd.Et[c]; m.dEpend[c] = 0.0;
+  }
+  h->ntwinned = hd.ntwinned;
+  CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));
+  rc = switch_to_voxel_classes(h);   // orientations may be anything now
+  if (rc) return rc;
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  h->have_micro = true;
+  return EVP_OK;
+}
+
 int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   if (!h || !out || comp < 0 || comp > 5) return EVP_ERR_ARG;
   if (h->nranks != 1) return fail(h, EVP_ERR_UNSUPPORTED, "debug_spectrum: single-rank handles only");

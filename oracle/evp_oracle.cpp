@@ -1043,6 +1043,54 @@ int evp_get_macro(evp_handle h, double emacro[6], double savg[6]) {
   return EVP_OK;
 }
 
+
+struct CkptHeader {
+  char magic[8];
+  int32_t nx, ny, nz, z0, nzl, nsmax, nranks, rank;
+  double Et[6], Edot_prev[6];
+  int64_t ntwinned;
+};
+
+int evp_save_state(evp_handle h, const char *path) {
+  if (!h || !path) return EVP_ERR_ARG;
+  std::FILE *f = std::fopen(path, "wb");
+  if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot write ") + path);
+  CkptHeader hd{};
+  std::memcpy(hd.magic, "EVPCKPT1", 8);
+  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.z0 = 0; hd.nzl = h->nz; hd.nsmax = h->nsmax; hd.nranks = 1; hd.rank = 0;
+  for (int c = 0; c < 6; ++c) { hd.Et[c] = h->Et[c]; hd.Edot_prev[c] = h->Edot_prev[c]; }
+  hd.ntwinned = h->ntwinned;
+  bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1;
+  auto wr = [&](const void *p, size_t bytes) { ok = ok && std::fwrite(p, 1, bytes, f) == bytes; };
+  const size_t N = h->N, ns = (size_t)std::max(h->nsmax, 1);
+  wr(h->sig.data(), 6 * N * 8); wr(h->e.data(), 6 * N * 8); wr(h->epsp.data(), 6 * N * 8); wr(h->crss.data(), ns * N * 8);
+  wr(h->rot.data(), 9 * N * 8); wr(h->gacc.data(), N * 8); wr(h->twinf.data(), ns * N * 8); wr(h->wrot.data(), 3 * N * 8);
+  wr(h->grain.data(), N * 4); wr(h->phase.data(), N * 4); wr(h->twinned.data(), N * 4);
+  std::fclose(f);
+  return ok ? EVP_OK : fail(h, EVP_ERR_ARG, "short write");
+}
+
+int evp_load_state(evp_handle h, const char *path) {
+  if (!h || !path) return EVP_ERR_ARG;
+  std::FILE *f = std::fopen(path, "rb");
+  if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot read ") + path);
+  CkptHeader hd{};
+  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT1", 8) == 0;
+  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nz || hd.nsmax != h->nsmax)) ok = false;
+  if (!ok) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint does not match this handle"); }
+  auto rd = [&](void *p, size_t bytes) { ok = ok && std::fread(p, 1, bytes, f) == bytes; };
+  const size_t N = h->N, ns = (size_t)std::max(h->nsmax, 1);
+  rd(h->sig.data(), 6 * N * 8); rd(h->e.data(), 6 * N * 8); rd(h->epsp.data(), 6 * N * 8); rd(h->crss.data(), ns * N * 8);
+  rd(h->rot.data(), 9 * N * 8); rd(h->gacc.data(), N * 8); rd(h->twinf.data(), ns * N * 8); rd(h->wrot.data(), 3 * N * 8);
+  rd(h->grain.data(), N * 4); rd(h->phase.data(), N * 4); rd(h->twinned.data(), N * 4);
+  std::fclose(f);
+  if (!ok) return fail(h, EVP_ERR_ARG, "short read");
+  for (int c = 0; c < 6; ++c) { h->Et[c] = hd.Et[c]; h->E[c] = hd.Et[c]; h->Edot_prev[c] = hd.Edot_prev[c]; h->dEpend[c] = 0; }
+  h->ntwinned = hd.ntwinned;
+  h->have_micro = true; h->in_incr = false;
+  return EVP_OK;
+}
+
 int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   if (!h || !out || comp < 0 || comp > 5) return EVP_ERR_ARG;
   const size_t NS = (size_t)h->nz * h->ny * h->nxh;
