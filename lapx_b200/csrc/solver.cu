@@ -872,26 +872,35 @@ int evp_set_reference_medium(evp_handle h, const double *c0) {
     CUDA_OK(h, cudaMemcpy(phs.data(), h->f.phase, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
     std::vector<double> Cm((size_t)36 * h->nphases);
     for (int p = 0; p < h->nphases; ++p) voigt_to_mandel(h->ph[p].c_voigt, &Cm[36 * p]);
+    // fixed blocks summed in block order: the result does not depend on the OpenMP thread count or schedule
     double acc[36] = {0};
-#pragma omp parallel for schedule(static) reduction(+ : acc[:36])
-    for (long long v = 0; v < N; ++v) {
-      double R[9], Q[36], T[36];
-      for (int k = 0; k < 9; ++k) R[k] = rot[(size_t)k * N + v];
-      mandel_rotation(R, Q);
-      const double *C = &Cm[36 * phs[v]];
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-          double s = 0;
-          for (int k = 0; k < 6; ++k) s += Q[6 * i + k] * C[6 * k + j];
-          T[6 * i + j] = s;
-        }
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-          double s = 0;
-          for (int k = 0; k < 6; ++k) s += T[6 * i + k] * Q[6 * j + k];
-          acc[6 * i + j] += s;
-        }
+    const long long kBlk = 4096, nblk = (N + kBlk - 1) / kBlk;
+    std::vector<double> part((size_t)36 * nblk, 0.0);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long long b = 0; b < nblk; ++b) {
+      double *pa = &part[(size_t)36 * b];
+      const long long v1 = std::min(N, (b + 1) * kBlk);
+      for (long long v = b * kBlk; v < v1; ++v) {
+        double R[9], Q[36], T[36];
+        for (int k = 0; k < 9; ++k) R[k] = rot[(size_t)k * N + v];
+        mandel_rotation(R, Q);
+        const double *C = &Cm[36 * phs[v]];
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) {
+            double x = 0;
+            for (int k = 0; k < 6; ++k) x += Q[6 * i + k] * C[6 * k + j];
+            T[6 * i + j] = x;
+          }
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) {
+            double x = 0;
+            for (int k = 0; k < 6; ++k) x += T[6 * i + k] * Q[6 * j + k];
+            pa[6 * i + j] += x;
+          }
+      }
     }
+    for (long long b = 0; b < nblk; ++b)
+      for (int k = 0; k < 36; ++k) acc[k] += part[(size_t)36 * b + k];
     if (h->nranks > 1) {
       CUDA_OK(h, cudaMemcpyAsync(h->d_totals + 16, acc, sizeof(acc), cudaMemcpyHostToDevice, h->st));
       int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 36, kNcclDouble, kNcclSum, h->comm, h->st);

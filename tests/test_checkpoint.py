@@ -46,10 +46,9 @@ def _phase(host):
 @pytest.mark.gpu
 def test_gpu_checkpoint_roundtrip_and_cross_backend(oracle_lib, product_lib, tmp_path):
     a, b, ra, rb = _roundtrip(product_lib, product_lib, product_lib, tmp_path)
-    # the continuing run finishes a transform that was enqueued speculatively before the checkpoint, the restarted one
-    # recomputes it: agreement is to rounding, not bitwise
-    assert rel_err(a.get_field(api.FIELD_STRESS), b.get_field(api.FIELD_STRESS)) < 1e-12
-    assert rel_err(ra.savg[:], rb.savg[:]) < 1e-12
+    # the CUDA path is deterministic (fixed-order reductions on device and host): the restart is bit identical
+    assert np.array_equal(a.get_field(api.FIELD_STRESS), b.get_field(api.FIELD_STRESS))
+    assert ra.savg[:] == rb.savg[:]
     # a checkpoint written by the CUDA path restarts the oracle (and the continued runs agree to 1e-8)
     c = _prepare(oracle_lib, product_lib)
     c.load_state(tmp_path / "state.ckpt")
