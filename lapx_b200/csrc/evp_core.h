@@ -259,7 +259,171 @@ struct ConstParams {
   double S0b[21];           // reference compliance, b-basis, packed (sample frame)
   double dt, tol_newton;
   int newton_itmax, iso_c0;
+  // uniform-exponent fast path (phase 0): dt * gamma0_s * n per system, and 1/n
+  double dtg0n[EVP_MAX_SYS];
+  double inv_n;
 };
+
+EVP_HD void fill_uniform_rate(const PhaseDev &P0, ConstParams &cp) {
+  for (int q = 0; q < EVP_MAX_SYS; ++q) cp.dtg0n[q] = (q < P0.nsys) ? cp.dt * P0.g0[q] * P0.nrate[q] : 0.0;
+  cp.inv_n = (P0.nsys > 0 && P0.nrate[0] > 0.0) ? 1.0 / P0.nrate[0] : 1.0;
+}
+
+// reciprocal of a pivot: hardware seed (>= 20 bits) + two Newton steps on the device (no slow-path call),
+// plain division on the host.  Pivots are compliances of order 1/modulus: never subnormal.
+EVP_HD double rcp_pivot(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / d;
+#endif
+}
+
+// LDL^T solve as ldl6_solve, with rcp_pivot for the six pivot reciprocals
+EVP_HD bool ldl6_solve_fast(double a[21], double b[6]) {
+  double invd[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double w[6];
+    double d = a[sidx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      w[k] = a[sidx(k, j)] * a[sidx(k, k)];
+      d -= a[sidx(k, j)] * w[k];
+    }
+    a[sidx(j, j)] = d;
+    ok = ok && (d > 0.0);
+    const double inv = rcp_pivot(d);
+    invd[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = a[sidx(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= a[sidx(k, i)] * w[k];
+      a[sidx(j, i)] = t * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) b[i] -= a[sidx(k, i)] * b[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[i] *= invd[i];
+#pragma unroll
+  for (int i = 4; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) b[i] -= a[sidx(i, k)] * b[k];
+  }
+  return ok;
+}
+
+// |x|^K for NQ values at once, level by level (independent chains side by side: instruction-level parallelism)
+template <int K, int NQ>
+EVP_HD void pow_ct_arr(const double (&x)[NQ], double (&r)[NQ]) {
+  if constexpr (K == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) r[q] = 1.0;
+  } else if constexpr (K == 1) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) r[q] = fabs(x[q]);
+  } else {
+    pow_ct_arr<K / 2, NQ>(x, r);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) r[q] *= r[q];
+    if constexpr (K & 1) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) r[q] *= fabs(x[q]);
+    }
+  }
+}
+
+// Row a4, uniform-exponent fast path (every system of the phase has the same integer n = NPOW_T + 1, NS_T systems,
+// NS_T a multiple of G).  Same Newton iteration and stop rule as newton_crystal_t; what differs is the arithmetic
+// organisation:
+//  * systems are processed G at a time, phase by phase (projection, power, tangent), so G independent dependency
+//    chains are in flight (the DFMA pipe is half rate with a long dependent-issue latency);
+//  * the plastic strain-rate term of the residual is taken from the tangent: edp is homogeneous of degree n in s, so
+//    dt*edp(s) = (1/n) A s with A = dt * d(edp)/ds (Euler; holds with the one-sided twin cut-off too) — 25 FMAs instead
+//    of 5*NS_T + NS_T;
+//  * dt*gamma0*n comes premultiplied from ConstParams; the signed ratio x = tau/tau_c carries the sign.
+template <int NS_T, int NPOW_T, bool TWIN, int G, class JB, class GV, class ITC>
+EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV g, double s[6], ITC itc, int *bad) {
+  static_assert(NS_T > 0 && NS_T % G == 0 && NPOW_T >= 0, "uniform fast path");
+  const double tol = cp.tol_newton;
+  const int itmax = cp.newton_itmax;
+  int it = 0;
+  while (it < itmax) {
+    double A[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) A[k] = 0.0;
+#pragma unroll
+    for (int q0 = 0; q0 < NS_T; q0 += G) {
+      double xs[G], w[G];
+#pragma unroll
+      for (int q = 0; q < G; ++q) xs[q] = P.m[q0 + q][0] * s[0];
+#pragma unroll
+      for (int c = 1; c < 5; ++c)
+#pragma unroll
+        for (int q = 0; q < G; ++q) xs[q] += P.m[q0 + q][c] * s[c];
+#pragma unroll
+      for (int q = 0; q < G; ++q) xs[q] *= itc(q0 + q);
+      pow_ct_arr<NPOW_T, G>(xs, w);
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        double t = w[q] * cp.dtg0n[q0 + q];
+        if (TWIN) t = (P.twin[q0 + q] != 0 && xs[q] <= 0.0) ? 0.0 : t;
+        w[q] = t * itc(q0 + q);   // dt * d(gamma_dot)/d(tau)
+      }
+#pragma unroll
+      for (int q = 0; q < G; ++q)
+#pragma unroll
+        for (int k = 0; k < 15; ++k) A[k] += w[q] * P.mm[q0 + q][k];
+    }
+    // F = g - Jb s - (1/n) A s ;  J = Jb + A
+    double J[21], F[6], As[5];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) F[i] = g(i);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) As[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) {
+        const double jb = Jb(sidx(i, j));
+        if (i < 5 && j < 5) {
+          const double a = A[s5idx(i, j)];
+          J[sidx(i, j)] = jb + a;
+          As[i] += a * s[j];
+          if (j != i) As[j] += a * s[i];
+        } else {
+          J[sidx(i, j)] = jb;
+        }
+        F[i] -= jb * s[j];
+        if (j != i) F[j] -= jb * s[i];
+      }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) F[i] -= cp.inv_n * As[i];
+    const bool ok = ldl6_solve_fast(J, F);
+    double dn = 0.0, sn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      s[i] += F[i];
+      dn += F[i] * F[i];
+      sn += s[i] * s[i];
+    }
+    ++it;
+    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
+    if (dn <= tol * tol * sn) break;
+  }
+  return it;
+}
 
 // rotate the packed reference compliance into the crystal frame: S0c = Q^T S0b Q, Q = diag(M, 1)
 EVP_HD void rotate_s0(const double *S0b, const double M[25], double out[21]) {

@@ -45,6 +45,12 @@ __device__ __forceinline__ void store5(const CUtensorMap *tm, const void *src, i
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void load1(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }   // writes performed (peer stores)
@@ -705,6 +711,110 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
   warp_partials_store<10>(vals, nit, partials, nw, gw0);
 }
 
+
+// K1, uniform-exponent fast path (one phase, NS_T systems, integer exponent NPOW_T + 1 for all of them).
+//  * the 18 + NS_T per-voxel streams (sig, e, eps_p, 1/tau_c) of the block are staged by 1 KB bulk copies
+//    (cp.async.bulk, one elected thread, mbarrier) while every thread gathers its orientation-class tables:
+//    no register is tied up by loads in flight, which is what allows MINB = 4 resident blocks without spills;
+//  * the staging area of sig/e/eps_p is reused for g and s_old once the thread has consumed its column;
+//  * Newton: newton_crystal_p (evp_core.h).
+// Shared memory (doubles x kCB): [21 Jb | 18 streams -> 6 g, 6 s_old | NS_T 1/tau_c] + mbarrier.
+template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G>
+__global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long long vbase, long long count, double *__restrict__ partials,
+                                                              long long nw, long long gw0, int pf_dist) {
+  extern __shared__ __align__(16) double smd[];
+  constexpr int NSTREAM = 18 + NS_T;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smd + (21 + NSTREAM) * kCB);
+  const int tid = threadIdx.x;
+  const long long vl = (long long)blockIdx.x * kCB + tid;
+  const long long v = vbase + vl;
+  const long long N = f.N;
+  const long long v0 = vbase + (long long)blockIdx.x * kCB;
+  const bool bulk = ((long long)(blockIdx.x + 1) * kCB <= count) && ((v0 & 1) == 0) && ((N & 1) == 0);
+  double *st = smd + 21 * kCB;   // stream s of the block at st + s*kCB
+  if (bulk) {
+    if (tid == 0) {
+      tma::mbar_init(bar, 1);
+      tma::fence_mbar_init();
+      tma::mbar_expect_tx(bar, NSTREAM * kCB * 8);
+    }
+    __syncthreads();   // barrier initialised before any copy can complete on it / any thread waits on it
+    if (tid < NSTREAM) {   // one 1 KB stream per thread
+      const int s = tid;
+      const double *src = (s < 6) ? f.sig + (long long)s * N : (s < 12) ? f.e + (long long)(s - 6) * N
+                          : (s < 18) ? f.epsp + (long long)(s - 12) * N : f.itc + (long long)(s - 18) * N;
+      tma::load1(st + s * kCB, src + v0, kCB * 8, bar);
+    }
+  } else if (vl < count) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st[c * kCB + tid] = f.sig[c * N + v];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st[(6 + c) * kCB + tid] = f.e[c * N + v];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st[(12 + c) * kCB + tid] = f.epsp[c * N + v];
+#pragma unroll
+    for (int s = 0; s < NS_T; ++s) st[(18 + s) * kCB + tid] = f.itc[(long long)s * N + v];
+  }
+  // L2 prefetch of the streams of the block that runs one residency wave later
+  {
+    const long long vp = vbase + ((long long)blockIdx.x + pf_dist) * kCB;
+    if (vp + kCB <= N) {
+      if (tid >= 32 && tid < 32 + NSTREAM) {
+        const int s = tid - 32;
+        const double *base = (s < 6) ? f.sig + (long long)s * N : (s < 12) ? f.e + (long long)(s - 6) * N
+                             : (s < 18) ? f.epsp + (long long)(s - 12) * N : f.itc + (long long)(s - 18) * N;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + vp), "r"(kCB * 8) : "memory");
+      } else if (tid == 32 + NSTREAM) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f.orient + vp), "r"(kCB * 4) : "memory");
+      }
+    }
+  }
+  double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
+  int nit = 0;
+  const bool active = vl < count;
+  const PhaseDev &P = c_phase[0];
+  const SmAcc jb{smd + tid}, gv{st + tid}, so{st + 6 * kCB + tid}, itc{st + 18 * kCB + tid};
+  const long long NO = f.norient;
+  long long oid = 0;
+  double sc[6];
+  double M[25];
+  if (active) {
+    oid = f.orient[v];
+    double jbv[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * NO + oid);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);
+#pragma unroll
+    for (int k = 0; k < 21; ++k) jb(k, jbv[k]);
+  }
+  if (bulk) tma::mbar_wait(bar, 0);
+  if (active) {
+    double sig[6], em[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sig[c] = st[c * kCB + tid];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) em[c] = st[(6 + c) * kCB + tid] - st[(12 + c) * kCB + tid];
+    constitutive_prep(c_cp, RegAcc25{M}, sig, em, gv, so, sc);   // writes g / s_old over this thread's sig / e column
+    int bad = 0;
+    nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G>(P, c_cp, jb, gv, sc, itc, &bad);
+    double ds, de;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
+    constitutive_finish(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      f.sig[c * N + v] = sig[c];
+      vals[2 + c] = sig[c];
+    }
+    vals[0] = ds;
+    vals[1] = de;
+    vals[8] = (double)nit;
+    vals[9] = (double)bad;
+  }
+  warp_partials_store<10>(vals, nit, partials, nw, gw0);
+}
+
 // second stage of the reductions: fixed-order two-level sum of the warp partials (deterministic)
 constexpr int kRedBlocks = 296;
 __global__ void __launch_bounds__(256) k_reduce1(const double *__restrict__ partials, long long nw, double *__restrict__ scratch) {
@@ -1056,13 +1166,46 @@ static void launch_const_t(const Fields &f, long long vbase, long long count, in
   k_constitutive_t<NS_T, NPOW_T, ONEPH, MINB><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32, pf > 0 ? pf : (1 << 30));
 }
 
+
+template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G>
+static void launch_const_p(const Fields &f, long long vbase, long long count, double *partials, cudaStream_t st) {
+  const int nb = (int)((count + kCB - 1) / kCB);
+  const size_t smem = (size_t)(21 + 18 + NS_T) * kCB * sizeof(double) + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+  static int pf = -1;
+  if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * MINB;
+  k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32, pf > 0 ? pf : (1 << 30));
+}
+
 // variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
 void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow,
-                         double *partials, cudaStream_t st) {
+                         int any_twin, double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
-  static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 3;   // tuning knob: resident blocks per SM
-  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 4) return launch_const_t<12, 9, true, 4>(f, vbase, count, nsmax, partials, st);
-  if (one && uniform_ns == 12 && uniform_npow == 9 && minb == 2) return launch_const_t<12, 9, true, 2>(f, vbase, count, nsmax, partials, st);
+  static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 0;   // tuning knobs
+  static const int grp = getenv("EVP_K1_G") ? atoi(getenv("EVP_K1_G")) : 0;
+  static const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel for A/B timing
+  if (one && !legacy && (uniform_npow == 9 || uniform_npow == 19)) {
+    if (uniform_ns == 12 && !any_twin) {
+      if (uniform_npow == 9) {
+        if (minb == 3 && grp == 4) return launch_const_p<12, 9, false, 3, 4>(f, vbase, count, partials, st);
+        if (minb == 3 && grp == 12) return launch_const_p<12, 9, false, 3, 12>(f, vbase, count, partials, st);
+        if (minb == 3) return launch_const_p<12, 9, false, 3, 6>(f, vbase, count, partials, st);
+        if (grp == 4) return launch_const_p<12, 9, false, 4, 4>(f, vbase, count, partials, st);
+        if (grp == 12) return launch_const_p<12, 9, false, 4, 12>(f, vbase, count, partials, st);
+        return launch_const_p<12, 9, false, 4, 6>(f, vbase, count, partials, st);
+      }
+      return launch_const_p<12, 19, false, 4, 6>(f, vbase, count, partials, st);
+    }
+    if (uniform_ns == 24) {
+      if (uniform_npow == 9) return launch_const_p<24, 9, true, 3, 6>(f, vbase, count, partials, st);
+      return launch_const_p<24, 19, true, 3, 6>(f, vbase, count, partials, st);
+    }
+  }
   if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, vbase, count, nsmax, partials, st);
   if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 3>(f, vbase, count, nsmax, partials, st);
   if (one && uniform_ns == 12) return launch_const_t<12, -2, true, 3>(f, vbase, count, nsmax, partials, st);

@@ -92,6 +92,7 @@ struct evp_solver {
   MacroDev *d_macro = nullptr, *h_macro = nullptr;  // h_macro pinned
   double *d_partials = nullptr, *d_totals = nullptr, *d_scratch = nullptr;
   int uniform_ns = 0, uniform_npow = -2;
+  bool any_twin = false;
   // The local slab is processed in `nchunks` z-chunks of nzc planes, each with its own sub-buffers, so that with
   // ranks > 1 the all-to-alls of one chunk run (on the communication stream) under the kernels of the others.
   struct Chunk {
@@ -345,7 +346,7 @@ int enqueue_back_chunk(evp_handle h, int i, bool plain = false) {
 
 void enqueue_const_chunk(evp_handle h, int i) {
   tbeg(h, 5, h->st);
-  launch_constitutive(h->f, h->ch[i].vbase, h->ch[i].count, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->d_partials, h->st);
+  launch_constitutive(h->f, h->ch[i].vbase, h->ch[i].count, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0, h->d_partials, h->st);
   tend(h);
 }
 
@@ -465,6 +466,7 @@ int upload_const(evp_handle h) {
   h->cp.dt = h->dt;
   h->cp.tol_newton = h->ctrl.tol_newton;
   h->cp.newton_itmax = h->ctrl.newton_itmax;
+  fill_uniform_rate(h->phd[0], h->cp);
   upload_const_params(h->cp);
   return EVP_OK;
 }
@@ -566,6 +568,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   CK(cudaMalloc(&S->f.wrot, sizeof(double) * 3 * N));
   CK(cudaMalloc(&S->f.twinned, sizeof(int32_t) * N));
   CK(cudaMalloc(&S->f.itc, sizeof(double) * ns * N));
+  S->any_twin = any_twin;
   if (any_twin) CK(cudaMalloc(&S->f.twinf, sizeof(double) * ns * N));
   CK(cudaMalloc(&S->f.grain, sizeof(int32_t) * N));
   CK(cudaMalloc(&S->f.phase, sizeof(int32_t) * N));

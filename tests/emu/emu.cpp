@@ -58,6 +58,18 @@ int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig
   constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
+// uniform-exponent fast path (k_constitutive_p): phased system loop, residual from the tangent
+template <int NS_T, int NPOW_T, bool TWIN, int G>
+int run_p(const PhaseDev &P, ConstParams &cp, const double *R, double *sig, const double *em, double *itc, double *ds, double *de,
+          int *bad) {
+  double M[25], jb[21], g[6], so[6], sc[6];
+  fill_uniform_rate(P, cp);
+  increment_invariants(P, cp, R, M, jb);
+  constitutive_prep(cp, ArrAcc{M}, sig, em, ArrAcc{g}, ArrAcc{so}, sc);
+  const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{itc}, bad);
+  constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
+  return nit;
+}
 }  // namespace
 
 
@@ -142,7 +154,7 @@ int emu_green_point(const double *c0_voigt, double x, double y, double z, int ze
 
 int emu_rot_b5(const double *R, double *M) { rot_b5(R, M); return 0; }
 
-// production (templated) form of k_constitutive_t: variant 0 = generic, 1 = <12,9>, 2 = <12,-2>, 3 = <24,9>, 4 = <12,19>, 5 = <24,19>, 6 = <24,-2>
+// production (templated) form of k_constitutive_t: variant 0 = generic, 11..15 = uniform-exponent fast path, 1 = <12,9>, 2 = <12,-2>, 3 = <24,9>, 4 = <12,19>, 5 = <24,19>, 6 = <24,-2>
 int emu_constitutive_t(int variant, const evp_phase *ph, const double *c0_voigt, const double *R, double *sig, const double *e,
                        const double *epsp, const double *crss, double dt, double tol, int itmax, double *ds, double *de, int *bad) {
   PhaseDev P;
@@ -164,6 +176,11 @@ int emu_constitutive_t(int variant, const evp_phase *ph, const double *c0_voigt,
     case 4: return run_t<12, 19>(P, cp, R, sig, em, itc, ds, de, bad);
     case 5: return run_t<24, 19>(P, cp, R, sig, em, itc, ds, de, bad);
     case 6: return run_t<24, -2>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 11: return run_p<12, 9, false, 6>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 12: return run_p<12, 9, true, 4>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 13: return run_p<24, 9, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 14: return run_p<12, 19, false, 6>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 15: return run_p<24, 19, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
     default: return run_t<0, -2>(P, cp, R, sig, em, itc, ds, de, bad);
   }
 }
