@@ -269,6 +269,12 @@ EVP_HD void fill_uniform_rate(const PhaseDev &P0, ConstParams &cp) {
   cp.inv_n = (P0.nsys > 0 && P0.nrate[0] > 0.0) ? 1.0 / P0.nrate[0] : 1.0;
 }
 
+// kn = dt*gamma0*n / tau_c^n for the uniform-exponent fast path (npow = n-1 integer)
+EVP_HD double rate_factor(double dtg0n, double crss, int npow) {
+  const double itc = 1.0 / crss;
+  return dtg0n * pow_nm1(itc, npow, 0.0) * itc;
+}
+
 // reciprocal of a pivot: hardware seed (>= 20 bits) + two Newton steps on the device (no slow-path call),
 // plain division on the host.  Pivots are compliances of order 1/modulus: never subnormal.
 EVP_HD double rcp_pivot(double d) {
@@ -352,9 +358,12 @@ EVP_HD void pow_ct_arr(const double (&x)[NQ], double (&r)[NQ]) {
 //  * the plastic strain-rate term of the residual is taken from the tangent: edp is homogeneous of degree n in s, so
 //    dt*edp(s) = (1/n) A s with A = dt * d(edp)/ds (Euler; holds with the one-sided twin cut-off too) — 25 FMAs instead
 //    of 5*NS_T + NS_T;
-//  * dt*gamma0*n comes premultiplied from ConstParams; the signed ratio x = tau/tau_c carries the sign.
-template <int NS_T, int NPOW_T, bool TWIN, int G, class JB, class GV, class ITC>
-EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV g, double s[6], ITC itc, int *bad) {
+//  * the per-voxel, per-system factor kn = dt*gamma0*n / tau_c^n is prepared once per increment (rate_factor above,
+//    k_prep_itc), so the tangent coefficient is one multiply after the power: no tau/tau_c ratio in the loop.
+//    Range: |tau|^(n-1) and tau_c^-n are formed separately; with n <= 20 and stresses below 1e12 in any unit system
+//    both stay far inside the fp64 range.
+template <int NS_T, int NPOW_T, bool TWIN, int G, class JB, class GV, class KN>
+EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV g, double s[6], KN kn, int *bad) {
   static_assert(NS_T > 0 && NS_T % G == 0 && NPOW_T >= 0, "uniform fast path");
   const double tol = cp.tol_newton;
   const int itmax = cp.newton_itmax;
@@ -365,21 +374,19 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
     for (int k = 0; k < 15; ++k) A[k] = 0.0;
 #pragma unroll
     for (int q0 = 0; q0 < NS_T; q0 += G) {
-      double xs[G], w[G];
+      double tau[G], w[G];
 #pragma unroll
-      for (int q = 0; q < G; ++q) xs[q] = P.m[q0 + q][0] * s[0];
+      for (int q = 0; q < G; ++q) tau[q] = P.m[q0 + q][0] * s[0];
 #pragma unroll
       for (int c = 1; c < 5; ++c)
 #pragma unroll
-        for (int q = 0; q < G; ++q) xs[q] += P.m[q0 + q][c] * s[c];
-#pragma unroll
-      for (int q = 0; q < G; ++q) xs[q] *= itc(q0 + q);
-      pow_ct_arr<NPOW_T, G>(xs, w);
+        for (int q = 0; q < G; ++q) tau[q] += P.m[q0 + q][c] * s[c];
+      pow_ct_arr<NPOW_T, G>(tau, w);   // |tau|^(n-1)
 #pragma unroll
       for (int q = 0; q < G; ++q) {
-        double t = w[q] * cp.dtg0n[q0 + q];
-        if (TWIN) t = (P.twin[q0 + q] != 0 && xs[q] <= 0.0) ? 0.0 : t;
-        w[q] = t * itc(q0 + q);   // dt * d(gamma_dot)/d(tau)
+        double t = w[q] * kn(q0 + q);   // dt * d(gamma_dot)/d(tau) = [dt gamma0 n / tau_c^n] |tau|^(n-1)
+        if (TWIN) t = (P.twin[q0 + q] != 0 && tau[q] <= 0.0) ? 0.0 : t;
+        w[q] = t;
       }
 #pragma unroll
       for (int q = 0; q < G; ++q)

@@ -581,18 +581,47 @@ __device__ __forceinline__ int warp_max(int v) {
   return v;
 }
 
-// per-warp partial sums (no block barrier): lane 0 of every warp stores NV sums and one max into the
-// SoA partial buffer  partials[k * nw + warp]
+// Recursive-halving butterfly: sums N per-lane values over the warp in N + O(log N) exchanges instead of 5 N.  At every
+// level the lanes of the upper half hand their lower slots to the partner and keep the upper ones (and vice versa), so
+// the number of live slots halves; from one slot on the exchange is a plain xor sum.  The summation tree is fixed.
+template <int N, int M>
+struct WarpHalve {
+  static __device__ __forceinline__ void run(double *v, int lane, int &base, int &cnt, int &dup) {
+    if constexpr (M > 0) {
+      if constexpr (N == 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], M);
+        dup |= M;
+        WarpHalve<1, M / 2>::run(v, lane, base, cnt, dup);
+      } else {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & M) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const double lo = v[i];
+          const double hi = (H + i < N) ? v[H + i] : 0.0;
+          const double send = up ? lo : hi, keep = up ? hi : lo;
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+        }
+        if (up) { base += H; cnt -= H; } else { cnt = min(cnt, H); }
+        WarpHalve<H, M / 2>::run(v, lane, base, cnt, dup);
+      }
+    }
+  }
+};
+
+// per-warp partial sums (no block barrier): NV sums and one max go into the SoA partial buffer
+// partials[k * nw + warp]; sum k is stored by the lane that ends up owning it in the butterfly
 template <int NV>
 __device__ __forceinline__ void warp_partials_store(const double vals[NV], int vmax, double *__restrict__ partials, long long nw,
                                                     long long gw0 = 0) {
   const int lane = threadIdx.x & 31;
   const long long gw = gw0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double v[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double s = warp_sum(vals[k]);
-    if (lane == 0) partials[(long long)k * nw + gw] = s;
-  }
+  for (int k = 0; k < NV; ++k) v[k] = vals[k];
+  int base = 0, cnt = NV, dup = 0;
+  WarpHalve<NV, 16>::run(v, lane, base, cnt, dup);
+  if (cnt >= 1 && (lane & dup) == 0) partials[(long long)base * nw + gw] = v[0];
   const int m = warp_max(vmax);
   if (lane == 0) partials[(long long)NV * nw + gw] = (double)m;
 }
@@ -625,9 +654,11 @@ __global__ void __launch_bounds__(kCB) k_prep_orient(Fields f) {
 #pragma unroll
   for (int k = 0; k < 21; ++k) f.jb[k * NO + o] = Jb[k];
 }
-__global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax) {
+// fast_npow < 0: itc = 1/tau_c (generic kernels);  >= 0: itc = dt*gamma0*n / tau_c^n (uniform-exponent fast path, n = fast_npow + 1)
+__global__ void __launch_bounds__(256) k_prep_itc(Fields f, int nsmax, int fast_npow) {
   const long long n = (long long)nsmax * f.N;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) f.itc[i] = 1.0 / f.crss[i];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    f.itc[i] = (fast_npow >= 0) ? rate_factor(c_cp.dtg0n[i / f.N], f.crss[i], fast_npow) : 1.0 / f.crss[i];
 }
 
 // K1.  NS_T > 0: unrolled system loop; NPOW_T >= 0: compile-time rate exponent; ONEPH: single phase
@@ -714,11 +745,12 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
 
 // K1, uniform-exponent fast path (one phase, NS_T systems, integer exponent NPOW_T + 1 for all of them).
 //  * the 18 + NS_T per-voxel streams (sig, e, eps_p, 1/tau_c) of the block are staged by 1 KB bulk copies
-//    (cp.async.bulk, one elected thread, mbarrier) while every thread gathers its orientation-class tables:
+//    (cp.async.bulk, one stream per thread, mbarrier) while every thread gathers its orientation-class tables:
 //    no register is tied up by loads in flight, which is what allows MINB = 4 resident blocks without spills;
 //  * the staging area of sig/e/eps_p is reused for g and s_old once the thread has consumed its column;
 //  * Newton: newton_crystal_p (evp_core.h).
-// Shared memory (doubles x kCB): [21 Jb | 18 streams -> 6 g, 6 s_old | NS_T 1/tau_c] + mbarrier.
+// Shared memory (doubles x kCB): [21 Jb | 18 streams -> 6 g, 6 s_old | NS_T rate factors] + mbarrier.
+// f.itc holds the rate factors dt*gamma0*n/tau_c^n here (k_prep_itc with fast_npow >= 0).
 template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G>
 __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long long vbase, long long count, double *__restrict__ partials,
                                                               long long nw, long long gw0, int pf_dist) {
@@ -732,6 +764,9 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
   const long long v0 = vbase + (long long)blockIdx.x * kCB;
   const bool bulk = ((long long)(blockIdx.x + 1) * kCB <= count) && ((v0 & 1) == 0) && ((N & 1) == 0);
   double *st = smd + 21 * kCB;   // stream s of the block at st + s*kCB
+  const bool active = vl < count;
+  long long oid = 0;
+  if (active) oid = f.orient[v];   // head of the only dependent load chain (class id -> class tables): issue it first
   if (bulk) {
     if (tid == 0) {
       tma::mbar_init(bar, 1);
@@ -771,15 +806,12 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
   }
   double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
   int nit = 0;
-  const bool active = vl < count;
   const PhaseDev &P = c_phase[0];
   const SmAcc jb{smd + tid}, gv{st + tid}, so{st + 6 * kCB + tid}, itc{st + 18 * kCB + tid};
   const long long NO = f.norient;
-  long long oid = 0;
   double sc[6];
   double M[25];
   if (active) {
-    oid = f.orient[v];
     double jbv[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) jbv[k] = __ldg(f.jb + k * NO + oid);
@@ -1183,27 +1215,35 @@ static void launch_const_p(const Fields &f, long long vbase, long long count, do
 }
 
 // variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
+// the uniform-exponent fast path (k_constitutive_p) applies to: one phase, every system with the same integer exponent
+// n in {10, 20}, and 12 systems without twins or 24 systems.  Returns n-1, or -1 when the generic kernels are used.
+int constitutive_fast_npow(int nphases, int uniform_ns, int uniform_npow, int any_twin) {
+  static const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel for A/B timing
+  if (legacy || nphases != 1 || (uniform_npow != 9 && uniform_npow != 19)) return -1;
+  if ((uniform_ns == 12 && !any_twin) || uniform_ns == 24) return uniform_npow;
+  return -1;
+}
+
 void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow,
                          int any_twin, double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
   static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 0;   // tuning knobs
   static const int grp = getenv("EVP_K1_G") ? atoi(getenv("EVP_K1_G")) : 0;
-  static const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel for A/B timing
-  if (one && !legacy && (uniform_npow == 9 || uniform_npow == 19)) {
+  if (constitutive_fast_npow(nphases, uniform_ns, uniform_npow, any_twin) >= 0) {
     if (uniform_ns == 12 && !any_twin) {
       if (uniform_npow == 9) {
-        if (minb == 3 && grp == 4) return launch_const_p<12, 9, false, 3, 4>(f, vbase, count, partials, st);
-        if (minb == 3 && grp == 12) return launch_const_p<12, 9, false, 3, 12>(f, vbase, count, partials, st);
-        if (minb == 3) return launch_const_p<12, 9, false, 3, 6>(f, vbase, count, partials, st);
-        if (grp == 4) return launch_const_p<12, 9, false, 4, 4>(f, vbase, count, partials, st);
-        if (grp == 12) return launch_const_p<12, 9, false, 4, 12>(f, vbase, count, partials, st);
-        return launch_const_p<12, 9, false, 4, 6>(f, vbase, count, partials, st);
+        if (minb == 3) return launch_const_p<12, 9, false, 3, 12>(f, vbase, count, partials, st);
+        return launch_const_p<12, 9, false, 4, 12>(f, vbase, count, partials, st);
       }
-      return launch_const_p<12, 19, false, 4, 6>(f, vbase, count, partials, st);
+      return launch_const_p<12, 19, false, 4, 12>(f, vbase, count, partials, st);
     }
     if (uniform_ns == 24) {
-      if (uniform_npow == 9) return launch_const_p<24, 9, true, 3, 6>(f, vbase, count, partials, st);
-      return launch_const_p<24, 19, true, 3, 6>(f, vbase, count, partials, st);
+      if (uniform_npow == 9) {
+        if (grp == 24) return launch_const_p<24, 9, true, 3, 24>(f, vbase, count, partials, st);
+        if (grp == 6) return launch_const_p<24, 9, true, 3, 6>(f, vbase, count, partials, st);
+        return launch_const_p<24, 9, true, 3, 12>(f, vbase, count, partials, st);
+      }
+      return launch_const_p<24, 19, true, 3, 12>(f, vbase, count, partials, st);
     }
   }
   if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, vbase, count, nsmax, partials, st);
@@ -1223,10 +1263,10 @@ __global__ void k_voxel_classes(Fields f) {
 }
 void launch_voxel_classes(const Fields &f, cudaStream_t st) { k_voxel_classes<<<592, 256, 0, st>>>(f); }
 
-void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st) {
+void launch_prep_increment(const Fields &f, int nsmax, int fast_npow, cudaStream_t st) {
   const int nb = (int)((f.norient + kCB - 1) / kCB);
   k_prep_orient<<<nb, kCB, 0, st>>>(f);
-  k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax);
+  k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax, fast_npow);
 }
 
 void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st) {

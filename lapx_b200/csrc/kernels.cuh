@@ -88,7 +88,8 @@ long long partial_doubles(long long N);
 int reduce_scratch_doubles();
 void launch_macro(const double *totals, MacroDev *macro, double ntot_global, cudaStream_t st);
 void launch_voxel_classes(const Fields &f, cudaStream_t st);
-void launch_prep_increment(const Fields &f, int nsmax, cudaStream_t st);
+void launch_prep_increment(const Fields &f, int nsmax, int fast_npow, cudaStream_t st);
+int constitutive_fast_npow(int nphases, int uniform_ns, int uniform_npow, int any_twin);
 void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st);
 void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaStream_t st);
 void launch_fill(double *p, long long n, double v, cudaStream_t st);

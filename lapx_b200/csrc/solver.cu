@@ -1002,7 +1002,7 @@ int evp_begin_increment(evp_handle h, double dt) {
     m.E[c] = h->Et[c] + m.dEpend[c];
   }
   m.iter = 0;
-  launch_prep_increment(h->f, h->nsmax, h->st);   // orientation / CRSS invariants of this increment
+  launch_prep_increment(h->f, h->nsmax, constitutive_fast_npow(h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0), h->st);   // orientation / CRSS invariants of this increment
   CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));  // E, Et, dEpend
   CUDA_OK(h, cudaMemcpyAsync(&h->d_macro->iter, &m.iter, sizeof(int), cudaMemcpyHostToDevice, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

@@ -64,9 +64,11 @@ int run_p(const PhaseDev &P, ConstParams &cp, const double *R, double *sig, cons
           int *bad) {
   double M[25], jb[21], g[6], so[6], sc[6];
   fill_uniform_rate(P, cp);
+  double kn[EVP_MAX_SYS];
+  for (int q = 0; q < NS_T; ++q) kn[q] = rate_factor(cp.dtg0n[q], 1.0 / itc[q], NPOW_T);   // k_prep_itc
   increment_invariants(P, cp, R, M, jb);
   constitutive_prep(cp, ArrAcc{M}, sig, em, ArrAcc{g}, ArrAcc{so}, sc);
-  const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{itc}, bad);
+  const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{kn}, bad);
   constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
