@@ -820,11 +820,28 @@ EVP_HD void pass16_store(double2 *s, int q, double2 v[16], OFF off, const double
     }
     if (R == 16) bfly16<INV>(&v[b * R]); else bfly8<INV>(&v[b * R]);
     const int base = (j - k) * R + k;
+    if (NS == 1) {
+      // first pass: a thread's R outputs are contiguous (base = R*j), so lanes with consecutive q hit the same
+      // shared-memory banks 1 KB apart.  Lanes with odd q store their outputs in a permuted order (partner r ^ SW
+      // lies in the other half of the 128-byte bank row): a warp then covers all 32 banks at every store.
+      const bool odd = (q & 1) != 0;
+      constexpr int SW = (R == 16) ? 4 : 1;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      // radix 16 leaves X[4 k1 + k2] at position k1 + 4 k2
-      const int xr = (R == 16) ? (4 * (r & 3) + (r >> 2)) : r;
-      s[off(base + xr * NS)] = v[b * R + r];
+      for (int r = 0; r < R; ++r) {
+        const int ra = r, rb = r ^ SW;
+        const int xa = (R == 16) ? (4 * (ra & 3) + (ra >> 2)) : ra;
+        const int xb = (R == 16) ? (4 * (rb & 3) + (rb >> 2)) : rb;
+        const double2 va = v[b * R + ra], vb = v[b * R + rb];
+        const double2 val = odd ? vb : va;
+        s[off(base + (odd ? xb : xa))] = val;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        // radix 16 leaves X[4 k1 + k2] at position k1 + 4 k2
+        const int xr = (R == 16) ? (4 * (r & 3) + (r >> 2)) : r;
+        s[off(base + xr * NS)] = v[b * R + r];
+      }
     }
   }
 }

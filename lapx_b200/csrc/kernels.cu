@@ -499,7 +499,6 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
     {
       const int ky = ky0 + yl;
       const int fy = (ky <= ny / 2) ? ky : ky - ny;
-      double *smd = reinterpret_cast<double *>(s);
 #pragma unroll 1
       for (int idx = tid; idx < C::CS; idx += C::T) {
         const int cc = idx % C::TX, kz = idx / C::TX;
@@ -511,11 +510,14 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
           const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
           double g[6];
           if (!nyq && !zero) green_G(c_green, x, y, z, scale, g);
+          double2 l2[6];   // 16-byte accesses: a warp reads 512 contiguous bytes per component
+#pragma unroll
+          for (int a = 0; a < 6; ++a) l2[a] = s[a * C::CS + idx];
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
             double lam[6], o[6];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) lam[a] = smd[2 * (a * C::CS + idx) + part];
+            for (int a = 0; a < 6; ++a) lam[a] = part ? l2[a].y : l2[a].x;
             if (zero) {
 #pragma unroll
               for (int a = 0; a < 6; ++a) o[a] = 0.0;
@@ -525,8 +527,10 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
               green_apply(g, x, y, z, lam, o);
             }
 #pragma unroll
-            for (int a = 0; a < 6; ++a) smd[2 * (a * C::CS + idx) + part] = o[a];
+            for (int a = 0; a < 6; ++a) { if (part) l2[a].y = o[a]; else l2[a].x = o[a]; }
           }
+#pragma unroll
+          for (int a = 0; a < 6; ++a) s[a * C::CS + idx] = l2[a];
         }
       }
     }
