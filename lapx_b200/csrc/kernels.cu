@@ -432,18 +432,26 @@ struct Z2Cfg {
   static constexpr int TX = (NZ >= 256) ? 4 : 8;
   static constexpr int R1 = NZ / 16;                    // first-pass radix (16 or 8)
   static constexpr int TPC = TX * NZ / 16;              // threads per component (64)
-  static constexpr int T = 6 * TPC;                     // all six components at once
+  static constexpr int T = 6 * TPC;                     // NB = 1: all six components at once
+  static constexpr int T2 = 3 * TPC;                    // NB = 2: a thread transforms components c and c + 3 in turn
   static constexpr int CS = NZ * TX;
   static constexpr size_t tile = (size_t)6 * CS * sizeof(double2);
-  static constexpr size_t smem = 2 * tile;
+  static constexpr size_t smem = 2 * tile;              // NB = 1: two tile buffers
+  static constexpr size_t smem2 = tile;                 // NB = 2: one tile buffer
 };
 
-template <int NZ>
-__global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
-                                                            int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
-                                                            int ny, double rx, double ry, double rz, double scale, int nkx, int ntiles,
-                                                            const double2 *__restrict__ twp) {
+// NB = 1: one block per SM, the next tile is prefetched into a second buffer while the current one is transformed.
+// NB = 2: two blocks per SM with one tile buffer each; a thread transforms components c and c + 3 one after the other
+//         (half the threads, same registers).  The two blocks drift apart, so the shared-memory-bound load/store phases
+//         of one overlap the fp64 butterflies, the Green operator and the TMA traffic of the other.
+template <int NZ, int NB>
+__global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_zfused2(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
+                                                             int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
+                                                             int ny, double rx, double ry, double rz, double scale, int nkx, int ntiles,
+                                                             const double2 *__restrict__ twp) {
   using C = Z2Cfg<NZ>;
+  constexpr int T = (NB == 1) ? C::T : C::T2;
+  constexpr int CPT = (NB == 1) ? 1 : 2;                // components per thread
   extern __shared__ __align__(128) double2 sm[];
   __shared__ uint64_t full[2];
   const int tid = threadIdx.x;
@@ -475,32 +483,44 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
   if (tid == 0 && tile < ntiles) issue_load(tile, 0);
   int n = 0;
   for (; tile < ntiles; tile += gridDim.x, ++n) {
-    const int buf = n & 1;
+    const int buf = (NB == 1) ? (n & 1) : 0;
     double2 *s = sm + (size_t)buf * 6 * C::CS;
     const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
-    // prefetch the next tile into the other buffer (its previous store has been read out: wait_read0 below)
-    if (tid == 0 && tile + gridDim.x < ntiles) {
-      tma::wait_read0();
-      issue_load(tile + gridDim.x, buf ^ 1);
+    if constexpr (NB == 1) {
+      // prefetch the next tile into the other buffer (its previous store has been read out: wait_read0 below)
+      if (tid == 0 && tile + gridDim.x < ntiles) {
+        tma::wait_read0();
+        issue_load(tile + gridDim.x, buf ^ 1);
+      }
+      tma::mbar_wait(&full[buf], (n >> 1) & 1);
+    } else {
+      tma::mbar_wait(&full[0], n & 1);
     }
-    tma::mbar_wait(&full[buf], (n >> 1) & 1);
-    const OffES<C::TX> off{c * C::CS + col};
     double2 v[16];
-    // forward: pass 1 (radix R1, no twiddles), pass 2 (radix 16)
-    pass16_load<NZ, C::R1>(s, q, v, off);
+    // forward: pass 1 (radix R1, no twiddles), pass 2 (radix 16).  The components of one thread take turns: the barrier
+    // between the loads and the stores of one component also orders the other component's stores before its next loads
+#pragma unroll
+    for (int h = 0; h < CPT; ++h) {
+      const OffES<C::TX> off{(c + 3 * h) * C::CS + col};
+      pass16_load<NZ, C::R1>(s, q, v, off);
+      __syncthreads();
+      pass16_store<NZ, C::R1, 1, false>(s, q, v, off, tw);
+    }
     __syncthreads();
-    pass16_store<NZ, C::R1, 1, false>(s, q, v, off, tw);
-    __syncthreads();
-    pass16_load<NZ, 16>(s, q, v, off);
-    __syncthreads();
-    pass16_store<NZ, 16, C::R1, false>(s, q, v, off, tw);
+#pragma unroll
+    for (int h = 0; h < CPT; ++h) {
+      const OffES<C::TX> off{(c + 3 * h) * C::CS + col};
+      pass16_load<NZ, 16>(s, q, v, off);
+      __syncthreads();
+      pass16_store<NZ, 16, C::R1, false>(s, q, v, off, tw);
+    }
     __syncthreads();
     // Green operator per frequency (row a2)
     {
       const int ky = ky0 + yl;
       const int fy = (ky <= ny / 2) ? ky : ky - ny;
 #pragma unroll 1
-      for (int idx = tid; idx < C::CS; idx += C::T) {
+      for (int idx = tid; idx < C::CS; idx += T) {
         const int cc = idx % C::TX, kz = idx / C::TX;
         const int kx = k0 + cc;
         if (kx < nxh) {
@@ -536,13 +556,21 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
     }
     __syncthreads();
     // inverse
-    pass16_load<NZ, C::R1>(s, q, v, off);
+#pragma unroll
+    for (int h = 0; h < CPT; ++h) {
+      const OffES<C::TX> off{(c + 3 * h) * C::CS + col};
+      pass16_load<NZ, C::R1>(s, q, v, off);
+      __syncthreads();
+      pass16_store<NZ, C::R1, 1, true>(s, q, v, off, tw);
+    }
     __syncthreads();
-    pass16_store<NZ, C::R1, 1, true>(s, q, v, off, tw);
-    __syncthreads();
-    pass16_load<NZ, 16>(s, q, v, off);
-    __syncthreads();
-    pass16_store<NZ, 16, C::R1, true>(s, q, v, off, tw);
+#pragma unroll
+    for (int h = 0; h < CPT; ++h) {
+      const OffES<C::TX> off{(c + 3 * h) * C::CS + col};
+      pass16_load<NZ, 16>(s, q, v, off);
+      __syncthreads();
+      pass16_store<NZ, 16, C::R1, true>(s, q, v, off, tw);
+    }
     tma::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -558,6 +586,14 @@ __global__ void __launch_bounds__(Z2Cfg<NZ>::T, 1) k_zfused2(const __grid_consta
             tma::store5(&tz.m[i], s + cc * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), cc, r);
         }
       tma::commit();
+      if constexpr (NB == 2) {
+        // single buffer: the next tile can land once the store has read this one out; the other block of the SM
+        // computes meanwhile
+        if (tile + gridDim.x < ntiles) {
+          tma::wait_read0();
+          issue_load(tile + gridDim.x, 0);
+        }
+      }
     }
   }
   if (tid == 0) { if (p2p) tma::wait_all0(); else tma::wait_read0(); }
@@ -1143,6 +1179,7 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
   static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16
+  static const int znb = getenv("EVP_ZNB") ? atoi(getenv("EVP_ZNB")) : 2;            // persistent kernel: resident blocks per SM (1 or 2)
   const bool fwd_only = mode == 1;
   if (mode == 0 && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {
     static int nsm = 0;
@@ -1150,13 +1187,23 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
     if (nz == 256) {
       using C = Z2Cfg<256>;
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
-      set_smem(C::smem, k_zfused2<256>);
-      k_zfused2<256><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      if (znb == 2) {
+        set_smem(C::smem2, k_zfused2<256, 2>);
+        k_zfused2<256, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      } else {
+        set_smem(C::smem, k_zfused2<256, 1>);
+        k_zfused2<256, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      }
     } else {
       using C = Z2Cfg<128>;
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
-      set_smem(C::smem, k_zfused2<128>);
-      k_zfused2<128><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      if (znb == 2) {
+        set_smem(C::smem2, k_zfused2<128, 2>);
+        k_zfused2<128, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      } else {
+        set_smem(C::smem, k_zfused2<128, 1>);
+        k_zfused2<128, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+      }
     }
     return;
   }
