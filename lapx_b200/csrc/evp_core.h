@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/evpfft.h"
 
 #if defined(__CUDACC__)
@@ -350,6 +352,60 @@ EVP_HD void pow_ct_arr(const double (&x)[NQ], double (&r)[NQ]) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FCC {111}<110> specialisation.  The twelve Schmid tensors in the b-basis are universal constants (no lattice
+// parameter enters): entries 0, +-1/(2 sqrt3), +-1/2, +-1/sqrt3, 16 of the 60 components and 76 of the 180 packed
+// products vanish.  With the table known at compile time the zero terms are never issued and the others are literal
+// operands.  Order and signs are those of evp_phase_fcc (host_tables.cpp); the solver only selects this path after
+// comparing the uploaded phase table with fcc_m() entry by entry (fcc_table_matches).
+// ---------------------------------------------------------------------------------------------
+EVP_HD constexpr double fcc_m(int q, int c) {
+  constexpr double a = 0.28867513459481288225, h = 0.5, t = 0.57735026918962576451;
+  constexpr double T[12][5] = {{a, -h, 0, -a, a},  {-a, -h, -a, 0, a}, {-t, 0, -a, a, 0}, {a, -h, 0, a, -a},
+                               {a, h, a, 0, a},    {t, 0, a, a, 0},    {-a, h, 0, a, a},  {-a, -h, a, 0, -a},
+                               {-t, 0, a, a, 0},   {a, -h, 0, a, a},   {-a, -h, a, 0, a}, {-t, 0, a, -a, 0}};
+  return T[q][c];
+}
+EVP_HD constexpr int s5row(int k) { return k < 5 ? 0 : (k < 9 ? 1 : (k < 12 ? 2 : (k < 14 ? 3 : 4))); }
+EVP_HD constexpr int s5col(int k) { return k - s5idx(s5row(k), s5row(k)) + s5row(k); }
+EVP_HD constexpr double fcc_mm(int q, int k) { return fcc_m(q, s5row(k)) * fcc_m(q, s5col(k)); }
+inline bool fcc_table_matches(const PhaseDev &P) {
+  if (P.nsys != 12) return false;
+  for (int q = 0; q < 12; ++q)
+    for (int c = 0; c < 5; ++c)
+      if (fabs(P.m[q][c] - fcc_m(q, c)) > 1e-14) return false;
+  return true;
+}
+// tau_q = m_q . s without the zero components
+template <int Q, int C, bool STARTED>
+EVP_HD double fcc_tau(const double *s, double acc) {
+  if constexpr (C == 5) {
+    return acc;
+  } else {
+    constexpr double v = fcc_m(Q, C);
+    if constexpr (v == 0.0) return fcc_tau<Q, C + 1, STARTED>(s, acc);
+    else if constexpr (!STARTED) return fcc_tau<Q, C + 1, true>(s, v * s[C]);
+    else return fcc_tau<Q, C + 1, true>(s, acc + v * s[C]);
+  }
+}
+// A += w * (m_q (x) m_q) without the zero products
+template <int Q, int K>
+EVP_HD void fcc_tangent(double *A, double w) {
+  if constexpr (K < 15) {
+    constexpr double v = fcc_mm(Q, K);
+    if constexpr (v != 0.0) A[K] += w * v;
+    fcc_tangent<Q, K + 1>(A, w);
+  }
+}
+template <int... Qs>
+EVP_HD void fcc_all_tau(const double *s, double *tau, std::integer_sequence<int, Qs...>) {
+  ((tau[Qs] = fcc_tau<Qs, 0, false>(s, 0.0)), ...);
+}
+template <int... Qs>
+EVP_HD void fcc_all_tangent(double *A, const double *w, std::integer_sequence<int, Qs...>) {
+  (fcc_tangent<Qs, 0>(A, w[Qs]), ...);
+}
+
 // Row a4, uniform-exponent fast path (every system of the phase has the same integer n = NPOW_T + 1, NS_T systems,
 // NS_T a multiple of G).  Same Newton iteration and stop rule as newton_crystal_t; what differs is the arithmetic
 // organisation:
@@ -362,9 +418,10 @@ EVP_HD void pow_ct_arr(const double (&x)[NQ], double (&r)[NQ]) {
 //    k_prep_itc), so the tangent coefficient is one multiply after the power: no tau/tau_c ratio in the loop.
 //    Range: |tau|^(n-1) and tau_c^-n are formed separately; with n <= 20 and stresses below 1e12 in any unit system
 //    both stay far inside the fp64 range.
-template <int NS_T, int NPOW_T, bool TWIN, int G, class JB, class GV, class KN>
+template <int NS_T, int NPOW_T, bool TWIN, int G, bool FCC, class JB, class GV, class KN>
 EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV g, double s[6], KN kn, int *bad) {
   static_assert(NS_T > 0 && NS_T % G == 0 && NPOW_T >= 0, "uniform fast path");
+  static_assert(!FCC || (NS_T == 12 && G == 12 && !TWIN), "FCC table: 12 systems, one group, no twins");
   const double tol = cp.tol_newton;
   const int itmax = cp.newton_itmax;
   int it = 0;
@@ -375,12 +432,16 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
 #pragma unroll
     for (int q0 = 0; q0 < NS_T; q0 += G) {
       double tau[G], w[G];
+      if constexpr (FCC) {
+        fcc_all_tau(s, tau, std::make_integer_sequence<int, 12>{});
+      } else {
 #pragma unroll
-      for (int q = 0; q < G; ++q) tau[q] = P.m[q0 + q][0] * s[0];
+        for (int q = 0; q < G; ++q) tau[q] = P.m[q0 + q][0] * s[0];
 #pragma unroll
-      for (int c = 1; c < 5; ++c)
+        for (int c = 1; c < 5; ++c)
 #pragma unroll
-        for (int q = 0; q < G; ++q) tau[q] += P.m[q0 + q][c] * s[c];
+          for (int q = 0; q < G; ++q) tau[q] += P.m[q0 + q][c] * s[c];
+      }
       pow_ct_arr<NPOW_T, G>(tau, w);   // |tau|^(n-1)
 #pragma unroll
       for (int q = 0; q < G; ++q) {
@@ -388,10 +449,14 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
         if (TWIN) t = (P.twin[q0 + q] != 0 && tau[q] <= 0.0) ? 0.0 : t;
         w[q] = t;
       }
+      if constexpr (FCC) {
+        fcc_all_tangent(A, w, std::make_integer_sequence<int, 12>{});
+      } else {
 #pragma unroll
-      for (int q = 0; q < G; ++q)
+        for (int q = 0; q < G; ++q)
 #pragma unroll
-        for (int k = 0; k < 15; ++k) A[k] += w[q] * P.mm[q0 + q][k];
+          for (int k = 0; k < 15; ++k) A[k] += w[q] * P.mm[q0 + q][k];
+      }
     }
     // F = g - Jb s - (1/n) A s ;  J = Jb + A
     double J[21], F[6], As[5];
