@@ -872,43 +872,57 @@ EVP_HD void pass16_load(const double2 *s, int q, double2 v[16], OFF off) {
     for (int r = 0; r < R; ++r) v[b * R + r] = s[off(j + r * (N / R))];
   }
 }
-// first pass (NS = 1, no twiddles) or second pass (NS = N/16, R = 16, hoisted twiddles tw[r] = W_N^(r*k), k = q)
-template <int N, int R, int NS, bool INV, class OFF>
-EVP_HD void pass16_store(double2 *s, int q, double2 v[16], OFF off, const double2 *tw) {
+// One Stockham pass of the 16-points-per-thread kernels: radix R in {2, 8, 16}, NS = product of the radices before it.
+// Twiddles W_N^(r*k*N/(NS*R)) with k = j % NS come from the accessor tw(r, k): the hoisted per-thread array of the last
+// pass (k = q there) or a table lookup for a middle pass.  SWZ: the outputs of a lane are stored in a permuted order
+// for lanes whose output group (j - k)/NS is odd — without it lanes of one warp write 64-byte pieces that all start in
+// the same half of the 128-byte bank row (two-way conflict on every store).
+template <int N, int R, int NS, bool INV, bool SWZ, class OFF, class TW>
+EVP_HD void pass16_store_t(double2 *s, int q, double2 v[16], OFF off, TW tw) {
 #pragma unroll
   for (int b = 0; b < 16 / R; ++b) {
     const int j = q + b * (N / 16);
     const int k = j % NS;
     if (NS > 1) {
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[b * R + r] = INV ? cmulc(v[b * R + r], tw[r]) : cmul(v[b * R + r], tw[r]);
+      for (int r = 1; r < R; ++r) {
+        const double2 w = tw(r, k);
+        v[b * R + r] = INV ? cmulc(v[b * R + r], w) : cmul(v[b * R + r], w);
+      }
     }
-    if (R == 16) bfly16<INV>(&v[b * R]); else bfly8<INV>(&v[b * R]);
+    if (R == 16) bfly16<INV>(&v[b * R]);
+    else if (R == 8) bfly8<INV>(&v[b * R]);
+    else bfly2<INV>(&v[b * R]);
     const int base = (j - k) * R + k;
-    if (NS == 1) {
-      // first pass: a thread's R outputs are contiguous (base = R*j), so lanes with consecutive q hit the same
-      // shared-memory banks 1 KB apart.  Lanes with odd q store their outputs in a permuted order (partner r ^ SW
-      // lies in the other half of the 128-byte bank row): a warp then covers all 32 banks at every store.
-      const bool odd = (q & 1) != 0;
+    if (SWZ) {
+      const bool odd = (((j - k) / NS) & 1) != 0;
       constexpr int SW = (R == 16) ? 4 : 1;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int ra = r, rb = r ^ SW;
-        const int xa = (R == 16) ? (4 * (ra & 3) + (ra >> 2)) : ra;
+        const int xa = (R == 16) ? (4 * (ra & 3) + (ra >> 2)) : ra;   // radix 16 leaves X[4 k1 + k2] at position k1 + 4 k2
         const int xb = (R == 16) ? (4 * (rb & 3) + (rb >> 2)) : rb;
         const double2 va = v[b * R + ra], vb = v[b * R + rb];
         const double2 val = odd ? vb : va;
-        s[off(base + (odd ? xb : xa))] = val;
+        s[off(base + (odd ? xb : xa) * NS)] = val;
       }
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        // radix 16 leaves X[4 k1 + k2] at position k1 + 4 k2
         const int xr = (R == 16) ? (4 * (r & 3) + (r >> 2)) : r;
         s[off(base + xr * NS)] = v[b * R + r];
       }
     }
   }
+}
+struct TwArr {   // hoisted twiddles of the last pass: tw[r] = W_N^(r*q)
+  const double2 *t;
+  EVP_HD double2 operator()(int r, int) const { return t[r]; }
+};
+// first pass (NS = 1, no twiddles) or last pass (NS = N/16, R = 16, hoisted twiddles tw[r] = W_N^(r*k), k = q)
+template <int N, int R, int NS, bool INV, class OFF>
+EVP_HD void pass16_store(double2 *s, int q, double2 v[16], OFF off, const double2 *tw) {
+  pass16_store_t<N, R, NS, INV, NS == 1>(s, q, v, off, TwArr{tw});
 }
 
 }  // namespace evp

@@ -94,6 +94,25 @@ void emu_fft16_n(double2 *s, int nlines, const double2 *twt) {
     }
 }
 
+// three-pass path of the persistent z kernel for N = 512: radix 2, 16, 16 (same 16 points per thread)
+struct TwMid { const double2 *t; int mult, n; double2 operator()(int r, int k) const { return t[(mult * r * k) % n]; } };
+template <int N, bool INV>
+void emu_fft16x3_n(double2 *s, int nlines, const double2 *twt) {
+  std::vector<double2> regs((size_t)nlines * (N / 16) * 16);
+  auto R = [&](int l, int q) { return &regs[((size_t)l * (N / 16) + q) * 16]; };
+  for (int l = 0; l < nlines; ++l) for (int q = 0; q < N / 16; ++q) pass16_load<N, 2>(s, q, R(l, q), OffLin{l * N});
+  for (int l = 0; l < nlines; ++l) for (int q = 0; q < N / 16; ++q) pass16_store_t<N, 2, 1, INV, true>(s, q, R(l, q), OffLin{l * N}, TwArr{nullptr});
+  for (int l = 0; l < nlines; ++l) for (int q = 0; q < N / 16; ++q) pass16_load<N, 16>(s, q, R(l, q), OffLin{l * N});
+  for (int l = 0; l < nlines; ++l) for (int q = 0; q < N / 16; ++q) pass16_store_t<N, 16, 2, INV, true>(s, q, R(l, q), OffLin{l * N}, TwMid{twt, N / 32, N});
+  for (int l = 0; l < nlines; ++l) for (int q = 0; q < N / 16; ++q) pass16_load<N, 16>(s, q, R(l, q), OffLin{l * N});
+  for (int l = 0; l < nlines; ++l)
+    for (int q = 0; q < N / 16; ++q) {
+      double2 tw[16];
+      for (int r = 0; r < 16; ++r) tw[r] = twt[(r * q) % N];   // NS = N/16: W_N^(r*k), k = q
+      pass16_store_t<N, 16, N / 16, INV, false>(s, q, R(l, q), OffLin{l * N}, TwArr{tw});
+    }
+}
+
 extern "C" {
 
 int emu_fft16(int n, int inv, int nlines, double *data) {
@@ -105,6 +124,7 @@ int emu_fft16(int n, int inv, int nlines, double *data) {
   double2 *s = reinterpret_cast<double2 *>(data);
   if (n == 128) { if (inv) emu_fft16_n<128, true>(s, nlines, tw.data()); else emu_fft16_n<128, false>(s, nlines, tw.data()); return 0; }
   if (n == 256) { if (inv) emu_fft16_n<256, true>(s, nlines, tw.data()); else emu_fft16_n<256, false>(s, nlines, tw.data()); return 0; }
+  if (n == 512) { if (inv) emu_fft16x3_n<512, true>(s, nlines, tw.data()); else emu_fft16x3_n<512, false>(s, nlines, tw.data()); return 0; }
   return -1;
 }
 

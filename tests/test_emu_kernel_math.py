@@ -34,7 +34,7 @@ def test_stockham_passes_match_numpy(emu, n, inv):
     assert np.abs(buf - ref).max() < 5e-13 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n", [128, 256])
+@pytest.mark.parametrize("n", [128, 256, 512])
 @pytest.mark.parametrize("inv", [0, 1])
 def test_radix16_passes_match_numpy(emu, n, inv):
     rng = np.random.default_rng(3 * n + inv)
