@@ -269,6 +269,7 @@ def main():
         r = s.equilibrium_iter()               # D2H: iteration report (norms, <sigma>, E) after a stream sync
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_newton_mean = r.newton_mean            # later in the increment than the value loop: fewer Newton steps per voxel
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -296,14 +297,19 @@ def main():
         kern.append({"name": k, "ms": round(float(kms[i]), 4), "algorithmic_bytes": int(ab[k]), "gbs": round(gbs, 1),
                      "frac_hbm": round(gbs / hbm, 4)})
     dom = max(range(6), key=lambda i: kms[i])
-    traffic = None
+    traffic, fp64 = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if list(tj.get("grid", [])) == list(local_grid) and KNAMES[dom] in tj and args.workload == "fcc":
             traffic = tj[KNAMES[dom]]["dram_bytes"]
+            if "fp64_pipe_pct" in tj[KNAMES[dom]]:
+                # second view of the same kernel (not timed here): share of cycles its fp64 pipe was busy in the committed
+                # ncu capture, against the DFMA peak measured with scratch/dfma_bench.cu on this pool
+                fp64 = {"pipe_active_pct_ncu": tj[KNAMES[dom]]["fp64_pipe_pct"], "peak_tflops_measured": tj["fp64_peak"]["tflops"],
+                        "source": tj[KNAMES[dom]]["source"]}
     roof = {"kernel": KNAMES[dom], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s",
-            "frac": kern[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
+            "frac": kern[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src, "fp64": fp64,
             "note": "constitutive is fp64-pipe bound (DESIGN.md §4); its HBM fraction is reported for uniformity"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -317,6 +323,7 @@ def main():
                              "d2h_seconds": round(t_down, 4)}},
         "roofline": roof, "kernels": kern, "exchange_ms": round(float(kms[6]), 4), "iter_ms_profiled": round(float(kms[7]), 4),
         "e2e": {"value": N * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 42 * 8, "d2h_bytes_per_step": 616,
+                "newton_mean": e2e_newton_mean,
                 "what": "evp_set_loading + evp_equilibrium_iter per step through the C ABI: BC upload, report download, host sync; "
                         "fields stay device resident by design (one-off transfer cost under config.setup)"},
         "gpu_launches": ((4 if world > 1 else 1) * 5 + 4) * args.steps,   # per iteration: 5 kernels per z-chunk + z pass + 2 reductions + macro
