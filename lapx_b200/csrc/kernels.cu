@@ -63,7 +63,7 @@ __constant__ ConstParams c_cp;
 static bool g_fcc_table = false;   // c_phase[0] is the canonical FCC {111}<110> table (compile-time specialisation allowed)
 void upload_phase_tables(const PhaseDev *ph, int nph) {
   cudaMemcpyToSymbol(c_phase, ph, sizeof(PhaseDev) * nph);
-  static const bool off = getenv("EVP_K1_FCC") && atoi(getenv("EVP_K1_FCC")) == 0;
+  const bool off = getenv("EVP_K1_FCC") && atoi(getenv("EVP_K1_FCC")) == 0;   // read per upload: tests switch it per solver
   g_fcc_table = !off && nph == 1 && fcc_table_matches(ph[0]);
 }
 void upload_green(const GreenConst &g) { cudaMemcpyToSymbol(c_green, &g, sizeof(g)); }
@@ -807,7 +807,8 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
   const long long v = vbase + vl;
   const long long N = f.N;
   const long long v0 = vbase + (long long)blockIdx.x * kCB;
-  const bool bulk = ((long long)(blockIdx.x + 1) * kCB <= count) && ((v0 & 1) == 0) && ((N & 1) == 0);
+  // pf_dist < 0 (EVP_K1_BULK=0, tests): per-thread loads for every block, the path partial / unaligned blocks take
+  const bool bulk = pf_dist >= 0 && ((long long)(blockIdx.x + 1) * kCB <= count) && ((v0 & 1) == 0) && ((N & 1) == 0);
   double *st = smd + 21 * kCB;   // stream s of the block at st + s*kCB
   const bool active = vl < count;
   long long oid = 0;
@@ -838,7 +839,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
   // L2 prefetch of the streams of the block that runs one residency wave later
   {
     const long long vp = vbase + ((long long)blockIdx.x + pf_dist) * kCB;
-    if (vp + kCB <= N) {
+    if (pf_dist >= 0 && vp + kCB <= N) {
       if (tid >= 32 && tid < 32 + NSTREAM) {
         const int s = tid - 32;
         const double *base = (s < 6) ? f.sig + (long long)s * N : (s < 12) ? f.e + (long long)(s - 6) * N
@@ -1267,14 +1268,15 @@ static void launch_const_p(const Fields &f, long long vbase, long long count, do
   }
   static int pf = -1;
   if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * MINB;
-  k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, FCC><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32, pf > 0 ? pf : (1 << 30));
+  const bool plain = getenv("EVP_K1_BULK") && atoi(getenv("EVP_K1_BULK")) == 0;
+  k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, FCC><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32,
+                                                                          plain ? -1 : (pf > 0 ? pf : (1 << 30)));
 }
 
-// variant selection: (all phases) same system count NS in {12, 24}, same integer exponent n-1 in {9, 19}, one phase
 // the uniform-exponent fast path (k_constitutive_p) applies to: one phase, every system with the same integer exponent
 // n in {10, 20}, and 12 systems without twins or 24 systems.  Returns n-1, or -1 when the generic kernels are used.
 int constitutive_fast_npow(int nphases, int uniform_ns, int uniform_npow, int any_twin) {
-  static const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel for A/B timing
+  const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel (A/B timing, tests)
   if (legacy || nphases != 1 || (uniform_npow != 9 && uniform_npow != 19)) return -1;
   if ((uniform_ns == 12 && !any_twin) || uniform_ns == 24) return uniform_npow;
   return -1;

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_final.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/smoke_final.log
+python bench.py --no-cpu-baseline > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+tail -n 3 gpurun_out/pytest_final.log; tail -n 2 gpurun_out/smoke_final.log

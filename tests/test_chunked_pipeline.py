@@ -45,3 +45,32 @@ def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
         outs.append((s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN), np.array(r.savg[:])))
     for a, b in zip(*outs):
         assert rel_err(a, b) < 1e-11
+
+
+@pytest.mark.parametrize("hcp", [False, True])
+def test_constitutive_kernel_variants_agree(hcp, product_lib, monkeypatch):
+    """k_constitutive_p (bulk-staged fast path; FCC: compile-time Schmid table) vs the same kernel with run-time tables
+    (EVP_K1_FCC=0) vs the thread-loads kernel k_constitutive_t (EVP_K1_LEGACY=1) vs the fast path without bulk staging
+    (EVP_K1_BULK=0: the per-thread loads partial blocks take): same Newton iteration, different arithmetic organisation
+    (DESIGN.md section 4)."""
+    outs = []
+    for env in ({}, {"EVP_K1_FCC": "0"}, {"EVP_K1_LEGACY": "1"}, {"EVP_K1_BULK": "0"}):
+        for k in ("EVP_K1_FCC", "EVP_K1_LEGACY", "EVP_K1_BULK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s, ids, grot = make_polycrystal(product_lib, product_lib, (32, 16, 16), 12, seed=9, hcp=hcp)
+        s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
+        s.set_loading(api.Loading.uniaxial_tension(1.0))
+        reps = []
+        for inc in range(2):
+            s.begin_increment(2e-4)
+            for it in range(6):
+                r = s.equilibrium_iter()
+                reps.append([r.err_stress, r.err_strain, *r.savg, *r.emacro, r.newton_max])
+            s.end_increment()
+        outs.append((np.array(reps), s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN), s.get_field(api.FIELD_CRSS)))
+        s.close()
+    for other in outs[1:]:
+        for a, b in zip(other, outs[0]):
+            assert rel_err(a, b) < 1e-10
