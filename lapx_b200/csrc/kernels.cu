@@ -1286,7 +1286,6 @@ void launch_constitutive(const Fields &f, long long vbase, long long count, int 
                          int any_twin, double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
   static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 0;   // tuning knobs
-  static const int grp = getenv("EVP_K1_G") ? atoi(getenv("EVP_K1_G")) : 0;
   if (constitutive_fast_npow(nphases, uniform_ns, uniform_npow, any_twin) >= 0) {
     if (uniform_ns == 12 && !any_twin) {
       if (uniform_npow == 9) {
@@ -1298,11 +1297,7 @@ void launch_constitutive(const Fields &f, long long vbase, long long count, int 
       return launch_const_p<12, 19, false, 4, 12>(f, vbase, count, partials, st);
     }
     if (uniform_ns == 24) {
-      if (uniform_npow == 9) {
-        if (grp == 24) return launch_const_p<24, 9, true, 3, 24>(f, vbase, count, partials, st);
-        if (grp == 6) return launch_const_p<24, 9, true, 3, 6>(f, vbase, count, partials, st);
-        return launch_const_p<24, 9, true, 3, 12>(f, vbase, count, partials, st);
-      }
+      if (uniform_npow == 9) return launch_const_p<24, 9, true, 3, 12>(f, vbase, count, partials, st);
       return launch_const_p<24, 19, true, 3, 12>(f, vbase, count, partials, st);
     }
   }
