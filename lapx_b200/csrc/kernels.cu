@@ -817,9 +817,10 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
     if (tid == 0) {
       tma::mbar_init(bar, 1);
       tma::fence_mbar_init();
-      tma::mbar_expect_tx(bar, NSTREAM * kCB * 8);
     }
     __syncthreads();   // barrier initialised before any copy can complete on it / any thread waits on it
+    // armed by lane 0 of warp 0 ahead of that warp's copies (program order); the single arrival keeps the phase open
+    if (tid == 0) tma::mbar_expect_tx(bar, NSTREAM * kCB * 8);
     if (tid < NSTREAM) {   // one 1 KB stream per thread
       const int s = tid;
       const double *src = (s < 6) ? f.sig + (long long)s * N : (s < 12) ? f.e + (long long)(s - 6) * N
