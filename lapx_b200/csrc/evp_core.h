@@ -376,35 +376,67 @@ inline bool fcc_table_matches(const PhaseDev &P) {
       if (fabs(P.m[q][c] - fcc_m(q, c)) > 1e-14) return false;
   return true;
 }
+// HCP, 24 systems in the order of evp_phase_hcp (3 prismatic<a>, 3 basal<a>, 12 pyramidal<c+a>, 6 tensile twins): the
+// VALUES depend on c/a, the ZERO PATTERN of the b-basis Schmid tensors does not (prismatic and basal slip touch two or
+// three of the five deviatoric components).  28 of the 120 components and 114 of the 360 packed products vanish; the
+// pattern is compiled in, the values stay run-time constants.  Selected after hcp24_pattern_matches().
+EVP_HD constexpr bool hcp24_nz(int q, int c) {
+  constexpr int M[24] = {0x11, 0x10, 0x11, 0x08, 0x0c, 0x0c, 0x1e, 0x1f, 0x1f, 0x1e, 0x1f, 0x1f,
+                         0x1f, 0x1f, 0x1e, 0x1f, 0x1f, 0x1e, 0x1f, 0x07, 0x1f, 0x1f, 0x07, 0x1f};   // bit c: component c may be non-zero
+  return ((M[q] >> c) & 1) != 0;
+}
+inline bool hcp24_pattern_matches(const PhaseDev &P) {
+  if (P.nsys != 24) return false;
+  for (int q = 0; q < 24; ++q)
+    for (int c = 0; c < 5; ++c)
+      if (!hcp24_nz(q, c) && fabs(P.m[q][c]) > 1e-14) return false;
+  return true;
+}
+
+// Structured Schmid tables.  TAB = 0: run-time tables, every term issued;  1: FCC literals;  2: HCP-24 zero pattern with
+// run-time values.
+template <int TAB>
+EVP_HD constexpr bool tab_nz(int q, int c) { return TAB == 1 ? fcc_m(q, c) != 0.0 : (TAB == 2 ? hcp24_nz(q, c) : true); }
+template <int TAB, int Q, int C>
+EVP_HD double tab_m(const PhaseDev &P) {
+  if constexpr (TAB == 1) { constexpr double v = fcc_m(Q, C); return v; }
+  else return P.m[Q][C];
+}
+template <int TAB, int Q, int K>
+EVP_HD double tab_mm(const PhaseDev &P) {
+  if constexpr (TAB == 1) { constexpr double v = fcc_mm(Q, K); return v; }
+  else return P.mm[Q][K];
+}
 // tau_q = m_q . s without the zero components
-template <int Q, int C, bool STARTED>
-EVP_HD double fcc_tau(const double *s, double acc) {
+template <int TAB, int Q, int C, bool STARTED>
+EVP_HD double tab_tau(const PhaseDev &P, const double *s, double acc) {
   if constexpr (C == 5) {
     return acc;
   } else {
-    constexpr double v = fcc_m(Q, C);
-    if constexpr (v == 0.0) return fcc_tau<Q, C + 1, STARTED>(s, acc);
-    else if constexpr (!STARTED) return fcc_tau<Q, C + 1, true>(s, v * s[C]);
-    else return fcc_tau<Q, C + 1, true>(s, acc + v * s[C]);
+    if constexpr (!tab_nz<TAB>(Q, C)) return tab_tau<TAB, Q, C + 1, STARTED>(P, s, acc);
+    else if constexpr (!STARTED) return tab_tau<TAB, Q, C + 1, true>(P, s, tab_m<TAB, Q, C>(P) * s[C]);
+    else return tab_tau<TAB, Q, C + 1, true>(P, s, acc + tab_m<TAB, Q, C>(P) * s[C]);
   }
 }
 // A += w * (m_q (x) m_q) without the zero products
-template <int Q, int K>
-EVP_HD void fcc_tangent(double *A, double w) {
+template <int TAB, int Q, int K>
+EVP_HD void tab_tangent(const PhaseDev &P, double *A, double w) {
   if constexpr (K < 15) {
-    constexpr double v = fcc_mm(Q, K);
-    if constexpr (v != 0.0) A[K] += w * v;
-    fcc_tangent<Q, K + 1>(A, w);
+    if constexpr (tab_nz<TAB>(Q, s5row(K)) && tab_nz<TAB>(Q, s5col(K))) A[K] += w * tab_mm<TAB, Q, K>(P);
+    tab_tangent<TAB, Q, K + 1>(P, A, w);
   }
 }
-template <int... Qs>
-EVP_HD void fcc_all_tau(const double *s, double *tau, std::integer_sequence<int, Qs...>) {
-  ((tau[Qs] = fcc_tau<Qs, 0, false>(s, 0.0)), ...);
+template <int TAB, int Q0, int... Qs>
+EVP_HD void tab_all_tau(const PhaseDev &P, const double *s, double *tau, std::integer_sequence<int, Qs...>) {
+  ((tau[Qs] = tab_tau<TAB, Q0 + Qs, 0, false>(P, s, 0.0)), ...);
 }
-template <int... Qs>
-EVP_HD void fcc_all_tangent(double *A, const double *w, std::integer_sequence<int, Qs...>) {
-  (fcc_tangent<Qs, 0>(A, w[Qs]), ...);
+template <int TAB, int Q0, int... Qs>
+EVP_HD void tab_all_tangent(const PhaseDev &P, double *A, const double *w, std::integer_sequence<int, Qs...>) {
+  (tab_tangent<TAB, Q0 + Qs, 0>(P, A, w[Qs]), ...);
 }
+// systems Q0 .. NS_T-1 of a structured table, G at a time: projection, power, tangent coefficient, tangent
+template <int TAB, int NS_T, int NPOW_T, bool TWIN, int G, int Q0, class KN>
+EVP_HD void tab_groups(const PhaseDev &P, const double *s, KN kn, double *A);
 
 // Row a4, uniform-exponent fast path (every system of the phase has the same integer n = NPOW_T + 1, NS_T systems,
 // NS_T a multiple of G).  Same Newton iteration and stop rule as newton_crystal_t; what differs is the arithmetic
@@ -418,10 +450,28 @@ EVP_HD void fcc_all_tangent(double *A, const double *w, std::integer_sequence<in
 //    k_prep_itc), so the tangent coefficient is one multiply after the power: no tau/tau_c ratio in the loop.
 //    Range: |tau|^(n-1) and tau_c^-n are formed separately; with n <= 20 and stresses below 1e12 in any unit system
 //    both stay far inside the fp64 range.
-template <int NS_T, int NPOW_T, bool TWIN, int G, bool FCC, class JB, class GV, class KN>
+template <int TAB, int NS_T, int NPOW_T, bool TWIN, int G, int Q0, class KN>
+EVP_HD void tab_groups(const PhaseDev &P, const double *s, KN kn, double *A) {
+  if constexpr (Q0 < NS_T) {
+    double tau[G], w[G];
+    tab_all_tau<TAB, Q0>(P, s, tau, std::make_integer_sequence<int, G>{});
+    pow_ct_arr<NPOW_T, G>(tau, w);   // |tau|^(n-1)
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      double t = w[q] * kn(Q0 + q);
+      if (TWIN) t = (P.twin[Q0 + q] != 0 && tau[q] <= 0.0) ? 0.0 : t;
+      w[q] = t;
+    }
+    tab_all_tangent<TAB, Q0>(P, A, w, std::make_integer_sequence<int, G>{});
+    tab_groups<TAB, NS_T, NPOW_T, TWIN, G, Q0 + G>(P, s, kn, A);
+  }
+}
+
+template <int NS_T, int NPOW_T, bool TWIN, int G, int TAB, class JB, class GV, class KN>
 EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV g, double s[6], KN kn, int *bad) {
   static_assert(NS_T > 0 && NS_T % G == 0 && NPOW_T >= 0, "uniform fast path");
-  static_assert(!FCC || (NS_T == 12 && G == 12 && !TWIN), "FCC table: 12 systems, one group, no twins");
+  static_assert(TAB != 1 || (NS_T == 12 && !TWIN), "FCC table: 12 systems, no twins");
+  static_assert(TAB != 2 || NS_T == 24, "HCP pattern: 24 systems");
   const double tol = cp.tol_newton;
   const int itmax = cp.newton_itmax;
   int it = 0;
@@ -429,29 +479,25 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
     double A[15];
 #pragma unroll
     for (int k = 0; k < 15; ++k) A[k] = 0.0;
+    if constexpr (TAB != 0) {
+      tab_groups<TAB, NS_T, NPOW_T, TWIN, G, 0>(P, s, kn, A);
+    } else {
 #pragma unroll
-    for (int q0 = 0; q0 < NS_T; q0 += G) {
-      double tau[G], w[G];
-      if constexpr (FCC) {
-        fcc_all_tau(s, tau, std::make_integer_sequence<int, 12>{});
-      } else {
+      for (int q0 = 0; q0 < NS_T; q0 += G) {
+        double tau[G], w[G];
 #pragma unroll
         for (int q = 0; q < G; ++q) tau[q] = P.m[q0 + q][0] * s[0];
 #pragma unroll
         for (int c = 1; c < 5; ++c)
 #pragma unroll
           for (int q = 0; q < G; ++q) tau[q] += P.m[q0 + q][c] * s[c];
-      }
-      pow_ct_arr<NPOW_T, G>(tau, w);   // |tau|^(n-1)
+        pow_ct_arr<NPOW_T, G>(tau, w);   // |tau|^(n-1)
 #pragma unroll
-      for (int q = 0; q < G; ++q) {
-        double t = w[q] * kn(q0 + q);   // dt * d(gamma_dot)/d(tau) = [dt gamma0 n / tau_c^n] |tau|^(n-1)
-        if (TWIN) t = (P.twin[q0 + q] != 0 && tau[q] <= 0.0) ? 0.0 : t;
-        w[q] = t;
-      }
-      if constexpr (FCC) {
-        fcc_all_tangent(A, w, std::make_integer_sequence<int, 12>{});
-      } else {
+        for (int q = 0; q < G; ++q) {
+          double t = w[q] * kn(q0 + q);   // dt * d(gamma_dot)/d(tau) = [dt gamma0 n / tau_c^n] |tau|^(n-1)
+          if (TWIN) t = (P.twin[q0 + q] != 0 && tau[q] <= 0.0) ? 0.0 : t;
+          w[q] = t;
+        }
 #pragma unroll
         for (int q = 0; q < G; ++q)
 #pragma unroll

@@ -60,11 +60,13 @@ __constant__ PhaseDev c_phase[EVP_MAX_PHASES];
 __constant__ GreenConst c_green;
 __constant__ ConstParams c_cp;
 
-static bool g_fcc_table = false;   // c_phase[0] is the canonical FCC {111}<110> table (compile-time specialisation allowed)
+// structure of c_phase[0] the fast path may compile in: 1 = canonical FCC {111}<110> table (literals), 2 = zero pattern of
+// the 24-system HCP table, 0 = none
+static int g_table = 0;
 void upload_phase_tables(const PhaseDev *ph, int nph) {
   cudaMemcpyToSymbol(c_phase, ph, sizeof(PhaseDev) * nph);
   const bool off = getenv("EVP_K1_FCC") && atoi(getenv("EVP_K1_FCC")) == 0;   // read per upload: tests switch it per solver
-  g_fcc_table = !off && nph == 1 && fcc_table_matches(ph[0]);
+  g_table = (off || nph != 1) ? 0 : (fcc_table_matches(ph[0]) ? 1 : (hcp24_pattern_matches(ph[0]) ? 2 : 0));
 }
 void upload_green(const GreenConst &g) { cudaMemcpyToSymbol(c_green, &g, sizeof(g)); }
 void upload_const_params(const ConstParams &p) { cudaMemcpyToSymbol(c_cp, &p, sizeof(p)); }
@@ -793,10 +795,11 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
 //    (cp.async.bulk, one stream per thread, mbarrier) while every thread gathers its orientation-class tables:
 //    no register is tied up by loads in flight, which is what allows MINB = 4 resident blocks without spills;
 //  * the staging area of sig/e/eps_p is reused for g and s_old once the thread has consumed its column;
-//  * Newton: newton_crystal_p (evp_core.h); FCC: Schmid tables as compile-time constants (zero terms never issued).
+//  * Newton: newton_crystal_p (evp_core.h); TAB: structure of the Schmid tables known at compile time (FCC: literal
+//    values; HCP-24: zero pattern) — zero terms are never issued.
 // Shared memory (doubles x kCB): [21 Jb | 18 streams -> 6 g, 6 s_old | NS_T rate factors] + mbarrier.
 // f.itc holds the rate factors dt*gamma0*n/tau_c^n here (k_prep_itc with fast_npow >= 0).
-template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G, bool FCC>
+template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G, int TAB>
 __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long long vbase, long long count, double *__restrict__ partials,
                                                               long long nw, long long gw0, int pf_dist) {
   extern __shared__ __align__(16) double smd[];
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
     for (int c = 0; c < 6; ++c) em[c] = st[(6 + c) * kCB + tid] - st[(12 + c) * kCB + tid];
     constitutive_prep(c_cp, RegAcc25{M}, sig, em, gv, so, sc);   // writes g / s_old over this thread's sig / e column
     int bad = 0;
-    nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G, FCC>(P, c_cp, jb, gv, sc, itc, &bad);
+    nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G, TAB>(P, c_cp, jb, gv, sc, itc, &bad);
     double ds, de;
 #pragma unroll
     for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
@@ -1257,20 +1260,20 @@ static void launch_const_t(const Fields &f, long long vbase, long long count, in
 }
 
 
-template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G, bool FCC = false>
+template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G, int TAB = 0>
 static void launch_const_p(const Fields &f, long long vbase, long long count, double *partials, cudaStream_t st) {
   const int nb = (int)((count + kCB - 1) / kCB);
   const size_t smem = (size_t)(21 + 18 + NS_T) * kCB * sizeof(double) + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, FCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, FCC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
   static int pf = -1;
   if (pf < 0) pf = getenv("EVP_K1_PF") ? atoi(getenv("EVP_K1_PF")) : 148 * MINB;
   const bool plain = getenv("EVP_K1_BULK") && atoi(getenv("EVP_K1_BULK")) == 0;
-  k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, FCC><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32,
+  k_constitutive_p<NS_T, NPOW_T, TWIN, MINB, G, TAB><<<nb, kCB, smem, st>>>(f, vbase, count, partials, num_warps(f.N), vbase / 32,
                                                                           plain ? -1 : (pf > 0 ? pf : (1 << 30)));
 }
 
@@ -1291,14 +1294,18 @@ void launch_constitutive(const Fields &f, long long vbase, long long count, int 
     if (uniform_ns == 12 && !any_twin) {
       if (uniform_npow == 9) {
         if (minb == 3) return launch_const_p<12, 9, false, 3, 12>(f, vbase, count, partials, st);
-        if (g_fcc_table) return launch_const_p<12, 9, false, 4, 12, true>(f, vbase, count, partials, st);
+        if (g_table == 1) return launch_const_p<12, 9, false, 4, 12, 1>(f, vbase, count, partials, st);
         return launch_const_p<12, 9, false, 4, 12>(f, vbase, count, partials, st);
       }
-      if (g_fcc_table) return launch_const_p<12, 19, false, 4, 12, true>(f, vbase, count, partials, st);
+      if (g_table == 1) return launch_const_p<12, 19, false, 4, 12, 1>(f, vbase, count, partials, st);
       return launch_const_p<12, 19, false, 4, 12>(f, vbase, count, partials, st);
     }
     if (uniform_ns == 24) {
-      if (uniform_npow == 9) return launch_const_p<24, 9, true, 3, 12>(f, vbase, count, partials, st);
+      if (uniform_npow == 9) {
+        if (g_table == 2) return launch_const_p<24, 9, true, 3, 12, 2>(f, vbase, count, partials, st);
+        return launch_const_p<24, 9, true, 3, 12>(f, vbase, count, partials, st);
+      }
+      if (g_table == 2) return launch_const_p<24, 19, true, 3, 12, 2>(f, vbase, count, partials, st);
       return launch_const_p<24, 19, true, 3, 12>(f, vbase, count, partials, st);
     }
   }

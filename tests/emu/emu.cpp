@@ -59,7 +59,7 @@ int run_t(const PhaseDev &P, const ConstParams &cp, const double *R, double *sig
   return nit;
 }
 // uniform-exponent fast path (k_constitutive_p): phased system loop, residual from the tangent
-template <int NS_T, int NPOW_T, bool TWIN, int G, bool FCC = false>
+template <int NS_T, int NPOW_T, bool TWIN, int G, int TAB = 0>
 int run_p(const PhaseDev &P, ConstParams &cp, const double *R, double *sig, const double *em, double *itc, double *ds, double *de,
           int *bad) {
   double M[25], jb[21], g[6], so[6], sc[6];
@@ -68,7 +68,7 @@ int run_p(const PhaseDev &P, ConstParams &cp, const double *R, double *sig, cons
   for (int q = 0; q < NS_T; ++q) kn[q] = rate_factor(cp.dtg0n[q], 1.0 / itc[q], NPOW_T);   // k_prep_itc
   increment_invariants(P, cp, R, M, jb);
   constitutive_prep(cp, ArrAcc{M}, sig, em, ArrAcc{g}, ArrAcc{so}, sc);
-  const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G, FCC>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{kn}, bad);
+  const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G, TAB>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{kn}, bad);
   constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
@@ -203,8 +203,10 @@ int emu_constitutive_t(int variant, const evp_phase *ph, const double *c0_voigt,
     case 13: return run_p<24, 9, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
     case 14: return run_p<12, 19, false, 6>(P, cp, R, sig, em, itc, ds, de, bad);
     case 15: return run_p<24, 19, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
-    case 16: if (!fcc_table_matches(P)) return -1; return run_p<12, 9, false, 12, true>(P, cp, R, sig, em, itc, ds, de, bad);
-    case 17: if (!fcc_table_matches(P)) return -1; return run_p<12, 19, false, 12, true>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 16: if (!fcc_table_matches(P)) return -1; return run_p<12, 9, false, 12, 1>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 17: if (!fcc_table_matches(P)) return -1; return run_p<12, 19, false, 12, 1>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 18: if (!hcp24_pattern_matches(P)) return -1; return run_p<24, 9, true, 12, 2>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 19: if (!hcp24_pattern_matches(P)) return -1; return run_p<24, 19, true, 12, 2>(P, cp, R, sig, em, itc, ds, de, bad);
     default: return run_t<0, -2>(P, cp, R, sig, em, itc, ds, de, bad);
   }
 }
