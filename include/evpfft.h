@@ -22,6 +22,9 @@
  *     engineering, shear components).
  *   - a handle is bound to one GPU and one stream; calls on a handle are stream ordered;
  *     reports are written after the stream has been synchronised.  Not thread-safe.
+ *   - ONE GPU PER PROCESS: kernel attributes and the __constant__ tables of the product library are
+ *     per-device state; evp_create on a second device of the same process fails with
+ *     EVP_ERR_UNSUPPORTED (multi-GPU runs use one process per GPU, see evp_dist).
  */
 #ifndef EVPFFT_H
 #define EVPFFT_H
@@ -33,7 +36,7 @@
 extern "C" {
 #endif
 
-#define EVP_ABI_VERSION 1
+#define EVP_ABI_VERSION 2
 #define EVP_MAX_SYS    32   /* slip + twin systems per phase (FCC 12, HCP 24..30) */
 #define EVP_MAX_MODES   8   /* deformation modes per phase                          */
 #define EVP_MAX_PHASES  4
@@ -75,13 +78,26 @@ typedef struct {
   double  twin_thr1, twin_thr2;         /* PTR thresholds                         */
 } evp_phase;
 
-/* Slab decomposition over z.  nranks = 1 for a single GPU. */
+/* Transport of the FFT transposes between ranks (evp_dist.transport). */
+typedef enum {
+  EVP_TRANSPORT_AUTO = 0,  /* peer-memory TMA stores when CUDA IPC mapping works on every rank, else NCCL */
+  EVP_TRANSPORT_NCCL = 1,  /* grouped ncclSend/ncclRecv all-to-all                                          */
+  EVP_TRANSPORT_P2P  = 2   /* peer-memory stores required: evp_create fails if IPC is unavailable          */
+} evp_transport_kind;
+
+/* Domain decomposition.  nranks = 1 for a single GPU.
+ *   py <= 1 : z-SLABS.  Rank r owns the planes z in [r*nz/nranks, (r+1)*nz/nranks); two transposes per iteration.
+ *   py >= 2 : PENCILS on a py x pz process grid (pz = nranks/py, rank = iy*pz + iz).  Rank (iy,iz) owns the block
+ *             y in [iy*ny/py, ...), z in [iz*nz/pz, ...), all x; four transposes per iteration (x<->y inside a row of
+ *             py ranks, y<->z inside a column of pz ranks).  NCCL transport only.                                   */
 typedef struct {
   int32_t nranks;
   int32_t rank;
   int32_t device;                       /* CUDA device ordinal for this rank      */
-  int32_t transport;                    /* 0 = NCCL all-to-all, 1 = peer-memory stores (IPC) */
+  int32_t transport;                    /* evp_transport_kind                     */
   uint8_t nccl_id[128];                 /* ncclUniqueId from evp_nccl_unique_id() */
+  int32_t py;                           /* 0/1 = slab, >= 2 = pencil rows         */
+  int32_t reserved[3];
 } evp_dist;
 
 typedef struct {
@@ -103,8 +119,9 @@ typedef struct {
   double  err_strain;                   /* <|eps(sig) - e|> / |E|            (a6) */
   double  savg[6];                      /* <sig>                                   */
   double  emacro[6];                    /* macroscopic strain E after a7           */
-  int32_t converged;
+  int32_t converged;                    /* tolerances met AND unconverged == 0    */
   int32_t nonfinite;                    /* voxels whose Newton produced a non-finite value */
+  int64_t unconverged;                  /* voxels whose Newton hit newton_itmax without meeting tol_newton (all ranks) */
 } evp_iter_report;
 
 typedef struct {
@@ -115,7 +132,8 @@ typedef struct {
   double  emacro[6];
   double  epavg[6];                     /* <eps_plastic> after commit             */
   double  seconds;                      /* wall time of the increment             */
-  double  twin_acc;                     /* accumulated twin volume fraction F_acc */
+  double  twin_acc;                     /* F_acc: twin volume fraction accumulated over the whole history (never decreases:
+                                           reorientation zeroes a voxel's fractions but not its contribution to F_acc) */
   double  twin_eff;                     /* reoriented volume fraction F_eff       */
   int64_t reoriented;                   /* voxels reoriented by this commit (all ranks) */
 } evp_step_report;
@@ -148,6 +166,9 @@ const char *evp_last_error(evp_handle h /* may be NULL: creation errors */);
 
 /* Local slab owned by this handle: z in [z0, z0+nzl). */
 int  evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl);
+/* Local block (pencil decomposition; for slabs y0 = 0, nyl = ny): fields passed to / returned by this handle are
+ * [component][z_local][y_local][x].                                                                             */
+int  evp_local_block(evp_handle h, int32_t *y0, int32_t *nyl, int32_t *z0, int32_t *nzl);
 /* Number of CRSS / twin-fraction components stored per voxel (max nsys over phases). */
 int  evp_nsys_max(evp_handle h);
 
@@ -224,8 +245,23 @@ int  evp_phase_hcp(evp_phase *out, double covera, const double c5[5] /* C11 C12 
 int  evp_voronoi(const evp_grid *g, int32_t ngrains, uint64_t seed, int32_t z0, int32_t nzl,
                  int32_t *grain_out, double *grain_rot9_out);
 int  evp_nccl_unique_id(uint8_t id[128]);
-/* 0 = single rank or NCCL all-to-all, 1 = peer-memory TMA stores (CUDA IPC). */
+/* Transport in use: EVP_TRANSPORT_NCCL (also for a single rank) or EVP_TRANSPORT_P2P. */
 int  evp_transport(evp_handle h);
+/* Hex digest of the sources this library was compiled from (lapx_b200/build.py embeds it; build() compares it
+ * with the digest of the sources in the tree, so that a stale binary is never what gets benchmarked).          */
+const char *evp_build_id(void);
+/* Kernel launches enqueued by this handle since creation (every __global__ launch of the library is counted). */
+int64_t evp_launch_count(evp_handle h);
+/* fp64 peak of the device the handle runs on, measured now: dependent-chain DFMA microbenchmark (8 chains per
+ * thread, 32 warps per SM, every SM), CUDA-event timed; best of `reps`.  The roofline denominator of the
+ * constitutive kernel ("fp64 peak to be measured").                                            */
+int  evp_debug_fp64_peak(evp_handle h, int32_t reps, double *tflops);
+/* Per-voxel text microstructure: one line per voxel "phi1 Phi phi2 i j k grain phase" with Bunge
+ * Euler angles in degrees, 1-based voxel indices (any order) and 1-based phase ids.  read: fills grain/phase
+ * [z][y][x] and rot9 [9][z][y][x] (crystal->sample); write: the inverse (angles recovered from rot9).            */
+int  evp_read_microstructure_txt(const char *path, const evp_grid *g, int32_t *grain, int32_t *phase, double *rot9);
+int  evp_write_microstructure_txt(const char *path, const evp_grid *g, const int32_t *grain, const int32_t *phase,
+                                  const double *rot9);
 
 #ifdef __cplusplus
 }

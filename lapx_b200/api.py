@@ -30,6 +30,8 @@ FIELD_STRESS, FIELD_STRAIN, FIELD_PLASTIC_STRAIN, FIELD_PLASTIC_RATE = 0, 1, 2, 
 FIELD_CRSS, FIELD_ROTATION, FIELD_GRAIN, FIELD_PHASE, FIELD_GAMMA_ACC = 4, 5, 6, 7, 8
 FIELD_TWIN_FRACTION, FIELD_STRAIN_INCR, FIELD_LOCAL_ROTATION, FIELD_TWINNED = 9, 10, 11, 12
 _INT_FIELDS = (FIELD_GRAIN, FIELD_PHASE, FIELD_TWINNED)
+# evp_transport_kind
+TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1, 2
 
 
 class EvpError(RuntimeError):
@@ -64,8 +66,10 @@ class Phase(C.Structure):
 
 
 class Dist(C.Structure):
+    """evp_dist: py <= 1 = z-slabs over nranks; py >= 2 = pencils on a py x (nranks/py) process grid."""
     _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("device", C.c_int32),
-                ("transport", C.c_int32), ("nccl_id", C.c_uint8 * 128)]
+                ("transport", C.c_int32), ("nccl_id", C.c_uint8 * 128),
+                ("py", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Ctrl(C.Structure):
@@ -79,7 +83,7 @@ class IterReport(C.Structure):
     _fields_ = [("iter", C.c_int32), ("newton_max", C.c_int32), ("newton_mean", C.c_double),
                 ("err_stress", C.c_double), ("err_strain", C.c_double),
                 ("savg", C.c_double * 6), ("emacro", C.c_double * 6),
-                ("converged", C.c_int32), ("nonfinite", C.c_int32)]
+                ("converged", C.c_int32), ("nonfinite", C.c_int32), ("unconverged", C.c_int64)]
 
 
 class StepReport(C.Structure):
@@ -98,8 +102,10 @@ ABI_SYMBOLS_COMMON = [
     "evp_step", "evp_equilibrium_iters", "evp_field_components", "evp_get_field",
     "evp_set_field", "evp_get_macro", "evp_debug_spectrum", "evp_stream",
     "evp_set_profiling", "evp_last_kernel_ms", "evp_transport", "evp_save_state", "evp_load_state",
+    "evp_local_block", "evp_build_id", "evp_launch_count", "evp_debug_fp64_peak",
 ]
-ABI_SYMBOLS_PRODUCT_ONLY = ["evp_phase_fcc", "evp_phase_hcp", "evp_voronoi", "evp_nccl_unique_id"]
+ABI_SYMBOLS_PRODUCT_ONLY = ["evp_phase_fcc", "evp_phase_hcp", "evp_voronoi", "evp_nccl_unique_id",
+                            "evp_read_microstructure_txt", "evp_write_microstructure_txt"]
 
 
 def _proto(lib):
@@ -143,6 +149,14 @@ def _proto(lib):
                            C.c_void_p, C.c_void_p], C.c_int),
         "evp_voronoi": ([P(Grid), C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
         "evp_nccl_unique_id": ([C.c_void_p], C.c_int),
+        "evp_local_block": ([H, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32)], C.c_int),
+        "evp_build_id": ([], C.c_char_p),
+        "evp_launch_count": ([H], C.c_int64),
+        "evp_debug_fp64_peak": ([H, C.c_int32, P(C.c_double)], C.c_int),
+        "evp_read_microstructure_txt": ([C.c_char_p, P(Grid), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "evp_write_microstructure_txt": ([C.c_char_p, P(Grid), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "evp_oracle_threads": ([], C.c_int),
+        "evp_oracle_set_threads": ([C.c_int], C.c_int),
     }
     for name, (args, res) in protos.items():
         try:
@@ -232,11 +246,11 @@ class Solver:
         if rc != 0:
             raise EvpError(rc, (lib.evp_last_error(None) or b"").decode())
         self.h = h
-        z0, nzl = C.c_int32(), C.c_int32()
-        self._check(lib.evp_local_slab(h, C.byref(z0), C.byref(nzl)))
-        self.z0, self.nzl = z0.value, nzl.value
+        y0, nyl, z0, nzl = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(lib.evp_local_block(h, C.byref(y0), C.byref(nyl), C.byref(z0), C.byref(nzl)))
+        self.y0, self.nyl, self.z0, self.nzl = y0.value, nyl.value, z0.value, nzl.value   # local block (slab: nyl = ny)
         self.nx, self.ny, self.nz = nx, ny, nz
-        self.nlocal = nx * ny * self.nzl
+        self.nlocal = nx * self.nyl * self.nzl
         self.nsys_max = lib.evp_nsys_max(h)
 
     # -- plumbing ------------------------------------------------------------------------
@@ -338,7 +352,7 @@ class Solver:
     def get_field(self, f: int) -> np.ndarray:
         nc = self.field_components(f)
         dt = np.int32 if f in _INT_FIELDS else np.float64
-        out = np.empty((nc, self.nzl, self.ny, self.nx), dtype=dt)
+        out = np.empty((nc, self.nzl, self.nyl, self.nx), dtype=dt)
         self._check(self.lib.evp_get_field(self.h, f, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
@@ -376,3 +390,14 @@ class Solver:
 
     def stream(self) -> int:
         return int(self.lib.evp_stream(self.h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.evp_launch_count(self.h))
+
+    def fp64_peak_tflops(self, reps: int = 5) -> float:
+        v = C.c_double()
+        self._check(self.lib.evp_debug_fp64_peak(self.h, int(reps), C.byref(v)))
+        return float(v.value)
+
+    def transport(self) -> str:
+        return "p2p" if self.lib.evp_transport(self.h) == TRANSPORT_P2P else "nccl"

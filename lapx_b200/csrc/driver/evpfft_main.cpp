@@ -111,35 +111,12 @@ bool read_deck(const std::string &path, Deck &d) {
   return true;
 }
 
-// Bunge Euler angles (degrees) -> crystal->sample rotation, row major
-static void euler_to_rot(double p1, double P, double p2, double *R) {
-  const double d2r = 3.14159265358979323846 / 180.0;
-  const double c1 = std::cos(p1 * d2r), s1 = std::sin(p1 * d2r), c = std::cos(P * d2r), s = std::sin(P * d2r), c2 = std::cos(p2 * d2r),
-               s2 = std::sin(p2 * d2r);
-  // g (sample->crystal) = Rz(p2) Rx(P) Rz(p1); crystal->sample = g^T
-  const double g[9] = {c1 * c2 - s1 * s2 * c, s1 * c2 + c1 * s2 * c, s2 * s, -c1 * s2 - s1 * c2 * c, -s1 * s2 + c1 * c2 * c, c2 * s, s1 * s, -c1 * s, c};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) R[3 * i + j] = g[3 * j + i];
-}
-
-// per-voxel text file: phi1 Phi phi2 i j k grain phase   (1-based voxel indices, x fastest or any order)
+// per-voxel text file "phi1 Phi phi2 i j k grain phase" (SURVEY.md §8(f).3): the library's reader, shared with the Python mirror
 bool read_micro_file(const Deck &d, std::vector<int32_t> &grain, std::vector<int32_t> &phase, std::vector<double> &rot9) {
-  std::ifstream in(d.micro_file);
-  if (!in) return fail("cannot open microstructure file " + d.micro_file);
   const size_t N = (size_t)d.grid.nx * d.grid.ny * d.grid.nz;
   grain.assign(N, -1); phase.assign(N, 0); rot9.assign(9 * N, 0.0);
-  double p1, P, p2; long i, j, k; int g, ph;
-  size_t n = 0;
-  while (in >> p1 >> P >> p2 >> i >> j >> k >> g >> ph) {
-    if (i < 1 || j < 1 || k < 1 || i > d.grid.nx || j > d.grid.ny || k > d.grid.nz) return fail("voxel index out of range in " + d.micro_file);
-    const size_t v = ((size_t)(k - 1) * d.grid.ny + (j - 1)) * d.grid.nx + (i - 1);
-    double R[9];
-    euler_to_rot(p1, P, p2, R);
-    for (int c = 0; c < 9; ++c) rot9[c * N + v] = R[c];
-    grain[v] = g; phase[v] = ph - 1 < 0 ? 0 : ph - 1;
-    ++n;
-  }
-  if (n != N) return fail("microstructure file has " + std::to_string(n) + " voxels, grid needs " + std::to_string(N));
+  if (evp_read_microstructure_txt(d.micro_file.c_str(), &d.grid, grain.data(), phase.data(), rot9.data()) != 0)
+    return fail("cannot read microstructure file " + d.micro_file + " (missing file, voxel index out of range, duplicate or missing voxels)");
   return true;
 }
 

@@ -211,6 +211,7 @@ EVP_HD void slip_rate_t(const PhaseDev &P, int s, double tau, double itc, double
 template <int NS_T, int NPOW_T, class JB, class GV, class ITC>
 EVP_HD int newton_crystal_t(const PhaseDev &P, JB Jb, GV g, double s[6], double dt, double tol, int itmax, ITC itc, int *bad) {
   int it = 0;
+  bool conv = false;
   while (it < itmax) {
     double A[15], F[6];
 #pragma unroll
@@ -250,9 +251,10 @@ EVP_HD int newton_crystal_t(const PhaseDev &P, JB Jb, GV g, double s[6], double 
       sn += s[i] * s[i];
     }
     ++it;
-    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
-    if (dn <= tol * tol * sn) break;
+    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; conv = true; break; }
+    if (dn <= tol * tol * sn) { conv = true; break; }
   }
+  if (!conv) *bad |= 2;   // itmax exhausted without meeting tol: the multiplier identity (a5) does not hold for this voxel
   return it;
 }
 
@@ -475,6 +477,7 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
   const double tol = cp.tol_newton;
   const int itmax = cp.newton_itmax;
   int it = 0;
+  bool conv = false;
   while (it < itmax) {
     double A[15];
 #pragma unroll
@@ -537,9 +540,10 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
       sn += s[i] * s[i];
     }
     ++it;
-    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; break; }
-    if (dn <= tol * tol * sn) break;
+    if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; conv = true; break; }
+    if (dn <= tol * tol * sn) { conv = true; break; }
   }
+  if (!conv) *bad |= 2;   // itmax exhausted without meeting tol: the multiplier identity (a5) does not hold for this voxel
   return it;
 }
 

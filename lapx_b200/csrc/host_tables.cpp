@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -117,9 +118,10 @@ int evp_phase_hcp(evp_phase *out, double ca, const double c5[5], int32_t with_tw
     }
   }
   int nmodes = 3;
-  if (with_twin >= 1) {  // tensile twin (10-12)[-1011]
+  if (with_twin >= 1) {  // {10-12} twin: shear along [-1011] (extension of c) for c/a < sqrt 3, reversed ([10-1-1]) above (Zn, Cd)
     const int pl[4] = {1, 0, -1, 2}, dr[4] = {-1, 0, 1, 1};
     hcp_plane(pl, ca, n0); hcp_dir(dr, ca, b0);
+    if (ca * ca > 3.0) for (double &v : b0) v = -v;
     for (int k = 0; k < 6; ++k) { rotz(b0, k, b); rotz(n0, k, n); set_sys(out, s++, b, n, 3); }
     out->twin[3] = 1;
     out->twin_shear[3] = std::fabs(ca * ca - 3.0) / (std::sqrt(3.0) * ca);
@@ -232,6 +234,81 @@ int evp_voronoi(const evp_grid *g, int32_t ngrains, uint64_t seed, int32_t z0, i
         grain_out[((size_t)(z - z0) * ny + y) * nx + x] = bid;
       }
   return EVP_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Per-voxel text microstructure: "phi1 Phi phi2 i j k grain phase", Bunge angles in degrees,
+// 1-based voxel indices in any order, 1-based phase ids.  The common exchange format of the EVPFFT / VPSC family
+// [literature; unverified for LApx, whose reader is not in the mount].
+// ---------------------------------------------------------------------------------------------
+static void bunge_to_rot(double p1, double P, double p2, double *R /* crystal -> sample, row major */) {
+  const double d2r = kPi / 180.0;
+  const double c1 = std::cos(p1 * d2r), s1 = std::sin(p1 * d2r), c = std::cos(P * d2r), s = std::sin(P * d2r), c2 = std::cos(p2 * d2r),
+               s2 = std::sin(p2 * d2r);
+  // g (sample -> crystal) = Rz(phi2) Rx(Phi) Rz(phi1); crystal -> sample = g^T
+  const double g[9] = {c1 * c2 - s1 * s2 * c, s1 * c2 + c1 * s2 * c, s2 * s, -c1 * s2 - s1 * c2 * c, -s1 * s2 + c1 * c2 * c, c2 * s, s1 * s, -c1 * s, c};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = g[3 * j + i];
+}
+static void rot_to_bunge(const double *R, double *p1, double *P, double *p2) {
+  // g = R^T;  g[2][2] = cos Phi, g[2][0] = s1 s, g[2][1] = -c1 s, g[0][2] = s2 s, g[1][2] = c2 s
+  const double r2d = 180.0 / kPi;
+  const double sP = std::sqrt(R[2] * R[2] + R[5] * R[5]);
+  const double Phi = std::atan2(sP, R[8]);
+  if (sP > 1e-9) {
+    *p1 = std::atan2(R[2], -R[5]) * r2d;    // g[2][0] = R[0][2], g[2][1] = R[1][2]
+    *p2 = std::atan2(R[6], R[7]) * r2d;     // g[0][2] = R[2][0], g[1][2] = R[2][1]
+  } else {                                  // Phi = 0 or 180: only phi1 +- phi2 is defined; put it all into phi1
+    *p1 = std::atan2(R[3], R[0]) * r2d;     // g[0][1] = R[1][0], g[0][0] = R[0][0]
+    *p2 = 0.0;
+  }
+  *P = Phi * r2d;
+}
+
+int evp_read_microstructure_txt(const char *path, const evp_grid *g, int32_t *grain, int32_t *phase, double *rot9) {
+  if (!path || !g || !grain || !rot9) return EVP_ERR_ARG;
+  std::FILE *f = std::fopen(path, "r");
+  if (!f) return EVP_ERR_ARG;
+  const size_t N = (size_t)g->nx * g->ny * g->nz;
+  std::vector<char> seen(N, 0);
+  double p1, P, p2;
+  long i, j, k;
+  int gr, ph;
+  size_t n = 0;
+  int rc = EVP_OK;
+  while (std::fscanf(f, "%lf %lf %lf %ld %ld %ld %d %d", &p1, &P, &p2, &i, &j, &k, &gr, &ph) == 8) {
+    if (i < 1 || j < 1 || k < 1 || i > g->nx || j > g->ny || k > g->nz) { rc = EVP_ERR_ARG; break; }
+    const size_t v = ((size_t)(k - 1) * g->ny + (j - 1)) * g->nx + (i - 1);
+    if (seen[v]) { rc = EVP_ERR_ARG; break; }   // a voxel listed twice
+    seen[v] = 1;
+    double R[9];
+    bunge_to_rot(p1, P, p2, R);
+    for (int c = 0; c < 9; ++c) rot9[c * N + v] = R[c];
+    grain[v] = gr;
+    if (phase) phase[v] = ph >= 1 ? ph - 1 : 0;
+    ++n;
+  }
+  std::fclose(f);
+  if (rc == EVP_OK && n != N) rc = EVP_ERR_ARG;   // missing voxels / trailing garbage
+  return rc;
+}
+
+int evp_write_microstructure_txt(const char *path, const evp_grid *g, const int32_t *grain, const int32_t *phase, const double *rot9) {
+  if (!path || !g || !grain || !rot9) return EVP_ERR_ARG;
+  std::FILE *f = std::fopen(path, "w");
+  if (!f) return EVP_ERR_ARG;
+  const size_t N = (size_t)g->nx * g->ny * g->nz;
+  for (int k = 0; k < g->nz; ++k)
+    for (int j = 0; j < g->ny; ++j)
+      for (int i = 0; i < g->nx; ++i) {
+        const size_t v = ((size_t)k * g->ny + j) * g->nx + i;
+        double R[9], p1, P, p2;
+        for (int c = 0; c < 9; ++c) R[c] = rot9[c * N + v];
+        rot_to_bunge(R, &p1, &P, &p2);
+        std::fprintf(f, "%.17g %.17g %.17g %d %d %d %d %d\n", p1, P, p2, i + 1, j + 1, k + 1, grain[v], phase ? phase[v] + 1 : 1);
+      }
+  return std::fclose(f) == 0 ? EVP_OK : EVP_ERR_ARG;
 }
 
 }  // extern "C"

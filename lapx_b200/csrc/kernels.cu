@@ -123,7 +123,7 @@ struct XCfg {
 
 template <int NX>
 __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__ sig, double2 *__restrict__ W, long long N,
-                                                      int rowbase, int nrows, SpecLayout Lay, int ny, const double2 *__restrict__ twp) {
+                                                      int rowbase, int nrows, SpecLayout Lay, const double2 *__restrict__ twp) {
   using C = XCfg<NX>;
   extern __shared__ double2 sm[];
   const int tid = threadIdx.x;
@@ -170,9 +170,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__
     const double2 zm = sm[ll * C::LS + ((NX - k) & (NX - 1))];
     const double2 A = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
     const double2 B = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
-    const int row = row0 + ll;
-    const int zl = row >> Lay.lg_nyl, y = row & (ny - 1);
-    const long long o = Lay.row_ysplit(2 * pair, zl, y) + k;
+    const long long o = Lay.row_x(2 * pair, row0 + ll, k);
     W[o] = A;
     W[o + Lay.cstride] = B;
   }
@@ -184,7 +182,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xfwd(const double *__restrict__
 template <int NX>
 __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict__ W, double *__restrict__ e, double *__restrict__ de_dbg,
                                                       const MacroDev *__restrict__ macro, long long N, int rowbase, int nrows, SpecLayout Lay,
-                                                      int ny, const double2 *__restrict__ twp) {
+                                                      const double2 *__restrict__ twp) {
   using C = XCfg<NX>;
   extern __shared__ double2 sm[];
   const int tid = threadIdx.x;
@@ -197,9 +195,7 @@ __global__ void __launch_bounds__(XCfg<NX>::T) k_xinv(const double2 *__restrict_
     const int ll = idx / nxh, k = idx % nxh;
     double2 A = make_double2(0.0, 0.0), B = A;
     if (ll < nrl) {
-      const int row = row0 + ll;
-      const int zl = row >> Lay.lg_nyl, y = row & (ny - 1);
-      const long long o = Lay.row_ysplit(2 * pair, zl, y) + k;
+      const long long o = Lay.row_x(2 * pair, row0 + ll, k);
       A = W[o];
       B = W[o + Lay.cstride];
     }
@@ -336,7 +332,7 @@ struct ZCfg {
 template <int NZ, int MODE>  // MODE 0: fused fwd+Green+inv; 1: forward only (evp_debug_spectrum); 2: fwd + local-rotation spectrum + inv
 __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo,
                                                                         int p2p, int lg_nzl, int lg_nzc, int zc,
-                                                                        int ky0, int nx, int ny, double rx, double ry, double rz,
+                                                                        int ky0, int kx0, int nx, int ny, double rx, double ry, double rz,
                                                                         double scale, const double2 *__restrict__ twp) {
   using C = ZCfg<NZ>;
   extern __shared__ __align__(128) double2 sm[];
@@ -374,7 +370,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
 #pragma unroll 1
     for (int idx = tid; idx < C::CS; idx += C::T) {
       const int cc = idx % C::TX, kz = idx / C::TX;
-      const int kx = k0 + cc;
+      const int kx = kx0 + k0 + cc;
       if (kx < nxh) {
         const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
         const double x = kx * rx, y = fy * ry, z = fz * rz;
@@ -453,7 +449,7 @@ struct Z2Cfg {
 //         of one overlap the fp64 butterflies, the Green operator and the TMA traffic of the other.
 template <int NZ, int NB>
 __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_zfused2(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
-                                                             int lg_nzl, int lg_nzc, int zc, int ky0, int nx,
+                                                             int lg_nzl, int lg_nzc, int zc, int ky0, int kx0, int nx,
                                                              int ny, double rx, double ry, double rz, double scale, int nkx, int ntiles,
                                                              const double2 *__restrict__ twp) {
   using C = Z2Cfg<NZ>;
@@ -529,7 +525,7 @@ __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_
 #pragma unroll 1
       for (int idx = tid; idx < C::CS; idx += T) {
         const int cc = idx % C::TX, kz = idx / C::TX;
-        const int kx = k0 + cc;
+        const int kx = kx0 + k0 + cc;
         if (kx < nxh) {
           const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
           const double x = kx * rx, y = fy * ry, z = fz * rz;
@@ -610,6 +606,7 @@ __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_
 // K1: constitutive update (rows a4, a5, a6).  One thread per voxel, 128 threads per block.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCB = 128;
+constexpr int kNSum = 11;   // per-voxel sums reduced over the grid (+ one max): partial slot layout [kNSum + 1][warps]
 int constitutive_block() { return kCB; }
 
 struct ItcSmem {
@@ -718,7 +715,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
   const long long vl = (long long)blockIdx.x * kCB + tid;   // index inside this z-chunk
   const long long v = vbase + vl;
   const long long N = f.N;
-  double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
+  double vals[kNSum] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, nonfinite, unconverged
   int nit = 0;
   // L2 prefetch of the per-voxel streams of the block that runs one residency wave later: with ~12 warps per SM
   // the loads below would otherwise expose DRAM latency (ncu: long-scoreboard stalls on their first use)
@@ -784,9 +781,10 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_t(Fields f, long lon
     vals[0] = ds;
     vals[1] = de;
     vals[8] = (double)nit;
-    vals[9] = (double)bad;
+    vals[9] = (double)(bad & 1);
+    vals[10] = (double)(bad >> 1);
   }
-  warp_partials_store<10>(vals, nit, partials, nw, gw0);
+  warp_partials_store<kNSum>(vals, nit, partials, nw, gw0);
 }
 
 
@@ -854,7 +852,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
       }
     }
   }
-  double vals[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, bad
+  double vals[kNSum] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ds, de, sig[6], nit, nonfinite, unconverged
   int nit = 0;
   const PhaseDev &P = c_phase[0];
   const SmAcc jb{smd + tid}, gv{st + tid}, so{st + 6 * kCB + tid}, itc{st + 18 * kCB + tid};
@@ -892,9 +890,10 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
     vals[0] = ds;
     vals[1] = de;
     vals[8] = (double)nit;
-    vals[9] = (double)bad;
+    vals[9] = (double)(bad & 1);
+    vals[10] = (double)(bad >> 1);
   }
-  warp_partials_store<10>(vals, nit, partials, nw, gw0);
+  warp_partials_store<kNSum>(vals, nit, partials, nw, gw0);
 }
 
 // second stage of the reductions: fixed-order two-level sum of the warp partials (deterministic)
@@ -904,13 +903,13 @@ __global__ void __launch_bounds__(256) k_reduce1(const double *__restrict__ part
   const int tid = threadIdx.x;
   const long long chunk = (nw + gridDim.x - 1) / gridDim.x;
   const long long w0 = (long long)blockIdx.x * chunk, w1 = (w0 + chunk < nw) ? w0 + chunk : nw;
-  for (int k = 0; k < 11; ++k) {
+  for (int k = 0; k <= kNSum; ++k) {
     double acc = 0.0;
-    for (long long w = w0 + tid; w < w1; w += 256) acc = (k < 10) ? acc + partials[(long long)k * nw + w] : fmax(acc, partials[(long long)k * nw + w]);
+    for (long long w = w0 + tid; w < w1; w += 256) acc = (k < kNSum) ? acc + partials[(long long)k * nw + w] : fmax(acc, partials[(long long)k * nw + w]);
     red[tid] = acc;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
-      if (tid < s) red[tid] = (k < 10) ? red[tid] + red[tid + s] : fmax(red[tid], red[tid + s]);
+      if (tid < s) red[tid] = (k < kNSum) ? red[tid] + red[tid + s] : fmax(red[tid], red[tid + s]);
       __syncthreads();
     }
     if (tid == 0) scratch[(long long)blockIdx.x * 16 + k] = red[0];
@@ -918,20 +917,20 @@ __global__ void __launch_bounds__(256) k_reduce1(const double *__restrict__ part
   }
 }
 // one warp per quantity: lanes stride over the stage-1 partials, fixed shuffle tree (deterministic)
-__global__ void __launch_bounds__(352) k_reduce2(const double *__restrict__ scratch, int nb, double *__restrict__ totals) {
+__global__ void __launch_bounds__(32 * (kNSum + 1)) k_reduce2(const double *__restrict__ scratch, int nb, double *__restrict__ totals) {
   const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double acc = 0.0;
-  for (int b = lane; b < nb; b += 32) acc = (k < 10) ? acc + scratch[(long long)b * 16 + k] : fmax(acc, scratch[(long long)b * 16 + k]);
+  for (int b = lane; b < nb; b += 32) acc = (k < kNSum) ? acc + scratch[(long long)b * 16 + k] : fmax(acc, scratch[(long long)b * 16 + k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double other = __shfl_xor_sync(0xffffffffu, acc, o);
-    acc = (k < 10) ? acc + other : fmax(acc, other);
+    acc = (k < kNSum) ? acc + other : fmax(acc, other);
   }
   if (lane == 0) totals[k] = acc;
 }
 
 // rows a6 (normalisation) + a7 (macro strain correction) on the device.
-// totals: [0] sum|dsig| [1] sum|S0 dsig| [2..7] sum sig [8] sum nit [9] bad [10] max nit
+// totals: [0] sum|dsig| [1] sum|S0 dsig| [2..7] sum sig [8] sum nit [9] non-finite [10] unconverged [11] max nit
 __global__ void k_macro(const double *__restrict__ totals, MacroDev *__restrict__ m, double ntot) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double sn = 0.0, en = 0.0;
@@ -945,8 +944,9 @@ __global__ void k_macro(const double *__restrict__ totals, MacroDev *__restrict_
   m->err_s = (sn > 0.0) ? es / sqrt(sn) : es;
   m->err_e = (en > 0.0) ? ee / sqrt(en) : ee;
   m->newton_mean = totals[8] / ntot;
-  m->newton_max = (int)totals[10];
+  m->newton_max = (int)totals[kNSum];
   m->nonfinite = (int)totals[9];
+  m->unconverged = (long long)totals[10];
   m->iter += 1;
   for (int a = 0; a < 6; ++a) {
     double acc = 0.0;
@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
   const long long v = (long long)blockIdx.x * kCB + tid;
   const long long N = f.N;
   const double dt = cp.dt;
-  double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] sum of twin fractions, [2..7] eps_p
+  double sums[kNSum] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] sum of current twin fractions, [1] twin fraction added by this increment, [2..7] eps_p
   if (v < N) {
     const PhaseDev &P = c_phase[f.phase[v]];
     double R[9], M[25], t[6], sb[6], sc[6];
@@ -996,7 +996,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
       for (int b = 0; b < 5; ++b) x += M[b * 5 + a] * sb[b];
       sc[a] = x;
     }
-    double edc[5] = {0, 0, 0, 0, 0}, dG = 0.0, wpc[3] = {0, 0, 0}, fsum = 0.0;
+    double edc[5] = {0, 0, 0, 0, 0}, dG = 0.0, wpc[3] = {0, 0, 0}, fsum = 0.0, dfsum = 0.0;
     const int ns = P.nsys;
     for (int s = 0; s < ns; ++s) {
       double tau = 0.0;
@@ -1012,9 +1012,11 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
       dg_sm[s * kCB + tid] = dg;
       dG += dg;
       if (cp.twinning && P.twin[s]) {
-        const double fnew = f.twinf[(long long)s * N + v] + gd * dt * P.itshear[s];
+        const double df = gd * dt * P.itshear[s];   // also for voxels already reoriented: F_acc is a history sum
+        const double fnew = f.twinf[(long long)s * N + v] + df;
         f.twinf[(long long)s * N + v] = fnew;
         fsum += fnew;
+        dfsum += df;
       }
     }
     double eds[6];
@@ -1035,6 +1037,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
       sums[2 + c] = ep;
     }
     sums[0] = fsum;
+    sums[1] = dfsum;
     const double G0 = f.gacc[v];
     if (dG > 0.0) {
       for (int s = 0; s < ns; ++s) {
@@ -1060,7 +1063,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
       for (int k = 0; k < 9; ++k) f.rot[k * N + v] = R[k];
     }
   }
-  warp_partials_store<10>(sums, 0, partials, nw);
+  warp_partials_store<kNSum>(sums, 0, partials, nw);
 }
 
 // PTR (Tome, Lebensohn, Kocks 1991): a voxel whose predominant twin system exceeds thr1 + thr2*ratio (ratio = F_eff/F_acc)
@@ -1068,7 +1071,7 @@ __global__ void __launch_bounds__(kCB) k_commit(Fields f, CommitParams cp, doubl
 __global__ void __launch_bounds__(kCB) k_twin_reorient(Fields f, double ratio, double *__restrict__ partials, long long nw) {
   const long long v = (long long)blockIdx.x * kCB + threadIdx.x;
   const long long N = f.N;
-  double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double sums[kNSum] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (v < N && !f.twinned[v]) {
     const PhaseDev &P = c_phase[f.phase[v]];
     const double thr = P.twin_thr1 + P.twin_thr2 * ratio;
@@ -1096,7 +1099,7 @@ __global__ void __launch_bounds__(kCB) k_twin_reorient(Fields f, double ratio, d
       sums[0] = 1.0;
     }
   }
-  warp_partials_store<10>(sums, 0, partials, nw);
+  warp_partials_store<kNSum>(sums, 0, partials, nw);
 }
 
 __global__ void k_fill(double *p, long long n, double v) {
@@ -1114,6 +1117,11 @@ __global__ void k_init_crss(Fields f, int nsmax) {
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
+// every __global__ launch of the library goes through one of the launch_* functions below and is counted here
+// (evp_launch_count: bench.py reports the launches inside its timed region from this counter)
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+
 bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
 
 // opt in to large dynamic shared memory (static + dynamic > 48 KB), once per kernel instantiation (the call is not free)
@@ -1138,35 +1146,33 @@ bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 
   }
 
 void launch_xfwd(int nx, const double *sig, double2 *W, long long N, int rowbase, int nrows, SpecLayout L, const double2 *tw,
-                 cudaStream_t st) {
-  const int ny = L.nyl;  // plain layout: nyl == ny
+                 cudaStream_t st) { g_launches += 1;
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
     set_smem(C::smem, k_xfwd<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
-    k_xfwd<NX><<<grid, C::T, C::smem, st>>>(sig, W, N, rowbase, nrows, L, ny, tw);                     \
+    k_xfwd<NX><<<grid, C::T, C::smem, st>>>(sig, W, N, rowbase, nrows, L, tw);                         \
   }
   EVP_DISPATCH_N(nx, X_)
 #undef X_
 }
 
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,
-                 SpecLayout L, const double2 *tw, cudaStream_t st) {
-  const int ny = L.nyl;
+                 SpecLayout L, const double2 *tw, cudaStream_t st) { g_launches += 1;
 #define X_(NX)                                                                                        \
   {                                                                                                   \
     using C = XCfg<NX>;                                                                               \
     set_smem(C::smem, k_xinv<NX>);                                                                    \
     dim3 grid((nrows + C::L - 1) / C::L, 3);                                                          \
-    k_xinv<NX><<<grid, C::T, C::smem, st>>>(W, e, de_dbg, macro, N, rowbase, nrows, L, ny, tw);        \
+    k_xinv<NX><<<grid, C::T, C::smem, st>>>(W, e, de_dbg, macro, N, rowbase, nrows, L, tw);            \
   }
   EVP_DISPATCH_N(nx, X_)
 #undef X_
 }
 
 void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
-                  const double2 *tw, cudaStream_t st) {
+                  const double2 *tw, cudaStream_t st) { g_launches += 1;
 #define Y_(NY)                                                                                        \
   {                                                                                                   \
     using C = YCfg<NY>;                                                                               \
@@ -1184,7 +1190,7 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout
 }
 
 void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p_, int lg_nzl, int lg_nzc, int zrun,
-                   int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) {
+                   int nxh /* local kx columns */, int kx0, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) { g_launches += 1;
   const int p2p = p2p_ ? 1 : 0;
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
@@ -1199,20 +1205,20 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
       if (znb == 2) {
         set_smem(C::smem2, k_zfused2<256, 2>);
-        k_zfused2<256, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+        k_zfused2<256, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
       } else {
         set_smem(C::smem, k_zfused2<256, 1>);
-        k_zfused2<256, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+        k_zfused2<256, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
       }
     } else {
       using C = Z2Cfg<128>;
       const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
       if (znb == 2) {
         set_smem(C::smem2, k_zfused2<128, 2>);
-        k_zfused2<128, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+        k_zfused2<128, 2><<<ntiles < 2 * nsm ? ntiles : 2 * nsm, C::T2, C::smem2, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
       } else {
         set_smem(C::smem, k_zfused2<128, 1>);
-        k_zfused2<128, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+        k_zfused2<128, 1><<<ntiles < nsm ? ntiles : nsm, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
       }
     }
     return;
@@ -1223,13 +1229,13 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
     dim3 grid((nxh + C::TX - 1) / C::TX, nyl);                                                        \
     if (fwd_only) {                                                                                   \
       set_smem(C::smem, k_zfused<NZ, 1>);                                                             \
-      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 1><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, tw); \
     } else if (mode == 2) {                                                                           \
       set_smem(C::smem, k_zfused<NZ, 2>);                                                             \
-      k_zfused<NZ, 2><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 2><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_zfused<NZ, 0>);                                                             \
-      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, nx, ny, rx, ry, rz, scale, tw); \
+      k_zfused<NZ, 0><<<grid, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(nz, Z_)
@@ -1240,11 +1246,11 @@ int ypass_tx() { return 8; }
 int zpass_tx(int nz) { return (nz >= 1024) ? 2 : ((nz >= 256) ? 4 : 8); }
 
 static long long num_warps(long long N) { return ((N + kCB - 1) / kCB) * (kCB / 32); }
-long long partial_doubles(long long N) { return 11 * num_warps(N); }
+long long partial_doubles(long long N) { return (kNSum + 1) * num_warps(N); }
 int reduce_scratch_doubles() { return kRedBlocks * 16; }
 
 template <int NS_T, int NPOW_T, bool ONEPH, int MINB>
-static void launch_const_t(const Fields &f, long long vbase, long long count, int nsmax, double *partials, cudaStream_t st) {
+static void launch_const_t(const Fields &f, long long vbase, long long count, int nsmax, double *partials, cudaStream_t st) { g_launches += 1;
   const int nb = (int)((count + kCB - 1) / kCB);
   const size_t smem = (size_t)(33 + (nsmax > 0 ? nsmax : 1)) * kCB * sizeof(double);
   static bool attr_done = false;
@@ -1261,7 +1267,7 @@ static void launch_const_t(const Fields &f, long long vbase, long long count, in
 
 
 template <int NS_T, int NPOW_T, bool TWIN, int MINB, int G, int TAB = 0>
-static void launch_const_p(const Fields &f, long long vbase, long long count, double *partials, cudaStream_t st) {
+static void launch_const_p(const Fields &f, long long vbase, long long count, double *partials, cudaStream_t st) { g_launches += 1;
   const int nb = (int)((count + kCB - 1) / kCB);
   const size_t smem = (size_t)(21 + 18 + NS_T) * kCB * sizeof(double) + 16;
   static bool attr_done = false;
@@ -1324,33 +1330,83 @@ __global__ void k_voxel_classes(Fields f) {
     f.orient_rep[v] = v;
   }
 }
-void launch_voxel_classes(const Fields &f, cudaStream_t st) { k_voxel_classes<<<592, 256, 0, st>>>(f); }
+void launch_voxel_classes(const Fields &f, cudaStream_t st) { g_launches += 1; k_voxel_classes<<<592, 256, 0, st>>>(f); }
 
-void launch_prep_increment(const Fields &f, int nsmax, int fast_npow, cudaStream_t st) {
+void launch_prep_increment(const Fields &f, int nsmax, int fast_npow, cudaStream_t st) { g_launches += 2;
   const int nb = (int)((f.norient + kCB - 1) / kCB);
   k_prep_orient<<<nb, kCB, 0, st>>>(f);
   k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax, fast_npow);
 }
 
-void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st) {
+void launch_commit(const Fields &f, int nsmax, double dt, const double wapp[3], int texture, int twinning, double *partials, cudaStream_t st) { g_launches += 1;
   const int nb = (int)((f.N + kCB - 1) / kCB);
   const size_t smem = (size_t)(nsmax > 0 ? nsmax : 1) * kCB * sizeof(double);
   CommitParams cp{dt, {wapp[0], wapp[1], wapp[2]}, texture, twinning};
   k_commit<<<nb, kCB, smem, st>>>(f, cp, partials, num_warps(f.N));
 }
-void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaStream_t st) {
+void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaStream_t st) { g_launches += 1;
   const int nb = (int)((f.N + kCB - 1) / kCB);
   k_twin_reorient<<<nb, kCB, 0, st>>>(f, ratio, partials, num_warps(f.N));
 }
 
-void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) {
+void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st) { g_launches += 2;
   const long long nw = num_warps(N);
   const int nb = (int)((nw < kRedBlocks) ? nw : kRedBlocks);
   k_reduce1<<<nb, 256, 0, st>>>(partials, nw, scratch);
-  k_reduce2<<<1, 352, 0, st>>>(scratch, nb, totals);
+  k_reduce2<<<1, 32 * (kNSum + 1), 0, st>>>(scratch, nb, totals);
 }
-void launch_macro(const double *totals, MacroDev *macro, double ntot, cudaStream_t st) { k_macro<<<1, 32, 0, st>>>(totals, macro, ntot); }
-void launch_fill(double *p, long long n, double v, cudaStream_t st) { k_fill<<<592, 256, 0, st>>>(p, n, v); }
-void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st) { k_init_crss<<<592, 256, 0, st>>>(f, nsmax); }
+void launch_macro(const double *totals, MacroDev *macro, double ntot, cudaStream_t st) { g_launches += 1; k_macro<<<1, 32, 0, st>>>(totals, macro, ntot); }
+void launch_fill(double *p, long long n, double v, cudaStream_t st) { g_launches += 1; k_fill<<<592, 256, 0, st>>>(p, n, v); }
+void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st) { g_launches += 1; k_init_crss<<<592, 256, 0, st>>>(f, nsmax); }
+
+
+// ---------------------------------------------------------------------------------------------
+// fp64 peak of this device, measured (evp_debug_fp64_peak): 8 dependent DFMA chains per thread, 32 warps per SM,
+// every SM busy for about 1 ms; CUDA events on the caller's stream, best of `reps`.  The denominator of the
+// constitutive kernel's roofline (MEASURED_PEAKS.json holds HBM and bf16 figures only).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, double a, double b, int iters) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-9 + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 1.2345e300) out[0] = s;   // never true: keeps the chains alive without a store per thread
+}
+double measure_fp64_peak(int reps, cudaStream_t st) {
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  double *out = nullptr;
+  if (cudaMalloc(&out, 8) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 1000, nb = nsm * 4, nt = 256;
+  g_launches += 1 + (reps > 0 ? reps : 1);
+  k_fp64_peak<<<nb, nt, 0, st>>>(out, 0.999999, 1e-7, 50);
+  double best = 0.0;
+  for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+    cudaEventRecord(e0, st);
+    k_fp64_peak<<<nb, nt, 0, st>>>(out, 0.999999, 1e-7, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * (double)iters * 16 * 8 * nt * nb / (ms * 1e-3) * 1e-12;
+    if (ms > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
 
 }  // namespace evp

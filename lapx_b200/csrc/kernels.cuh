@@ -24,10 +24,18 @@ namespace evp {
 //   z-split view : addr(c, z, yl)   = (z / nzl) * dstride + c * cstride + (z % nzl) * zstride + yl * nxp
 // with cstride = nzl*nyl*nxp, zstride = nyl*nxp, dstride = 6*cstride.  Single GPU: nyl = ny, nzl = nz.
 // ---------------------------------------------------------------------------------------------
+// x-stage view (k_xfwd output / k_xinv input; pencil decomposition: kx pieces grouped by the rank of the row that owns them):
+//   addr(c, row, k)   = (k / kxl) * dstride + c * cstride + row * kxl + (k % kxl),  row = zl * nyl + y_local.
+// Slab / single GPU: kxl = nxp, i.e. the plain layout.
 struct SpecLayout {
-  int nyl, nzl, nxp, nxh;
+  int nyl, nzl, nxp, nxh;      // nxp: row pitch (= kxl), nxh: nx/2 + 1 (global)
   int lg_nyl, lg_nzl;          // all extents are powers of two: divisions become shifts
   long long cstride, zstride, dstride;
+  __host__ __device__ long long row_x(int c, int row, int k) const {
+    int j = 0;
+    while (k >= nxp) { k -= nxp; ++j; }   // at most py - 1 rounds; never taken for slabs
+    return (long long)j * dstride + (long long)c * cstride + (long long)row * nxp + k;
+  }
   __host__ __device__ long long row_ysplit(int c, int zl, int y) const {
     return (long long)(y >> lg_nyl) * dstride + (long long)c * cstride + (long long)zl * zstride + (long long)(y & (nyl - 1)) * nxp;
   }
@@ -43,6 +51,7 @@ struct MacroDev {
   double err_s, err_e, newton_mean;
   double epavg[6];
   int newton_max, nonfinite, iter, pad;
+  long long unconverged;
 };
 
 struct Fields {
@@ -76,7 +85,8 @@ struct ZOutMaps { CUtensorMap m[kMaxRanks * kMaxChunksP2P]; };   // z pass outpu
 void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
 void launch_zfused(int nz, int mode /* 0 Green, 1 forward only, 2 local rotation */, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p, int lg_nzl, int lg_nzc, int zrun,
-                   int nxh, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st);
+                   int nxv /* local kx columns */, int kx0 /* first global kx */, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw,
+                   cudaStream_t st);
 int ypass_tx();
 int zpass_tx(int nz);
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,
@@ -95,6 +105,8 @@ void launch_twin_reorient(const Fields &f, double ratio, double *partials, cudaS
 void launch_fill(double *p, long long n, double v, cudaStream_t st);
 void launch_init_crss(const Fields &f, int nsmax, cudaStream_t st);
 bool fft_size_supported(int n);
+long long launch_count();
+double measure_fp64_peak(int reps, cudaStream_t st);   // TFLOP/s, dependent-chain DFMA microbenchmark
 int constitutive_block();
 
 }  // namespace evp

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -22,9 +23,14 @@
 using namespace evp;
 using namespace evp::host;
 
+#ifndef EVP_SRC_HASH
+#define EVP_SRC_HASH "unknown"
+#endif
+
 namespace {
 
 std::string g_create_error;
+int g_device = -1;   // the one device this process drives (kernel attributes / __constant__ tables are per device)
 
 // ---- NCCL through dlopen (torch's bundled libnccl.so.2 if the process already loaded it) ----
 struct Id128 { char b[128]; };
@@ -79,7 +85,10 @@ struct evp_solver {
   evp_grid g{};
   int nx = 0, ny = 0, nz = 0, nxh = 0, nxp = 0;
   int nranks = 1, rank = 0, device = 0;
-  int nzl = 0, z0 = 0, nyl = 0, ky0 = 0;
+  // decomposition: process grid py x pz, rank = iy*pz + iz (slab: py = 1).  Real space: block [nzl][nyb][nx] at (z0, y0);
+  // y stage: [nzl][ny][kxl] at kx0 (nxv valid columns);  z stage: [nz][nyl][kxl] at (ky0, kx0)
+  int py = 1, pz = 1, iy = 0, iz = 0;
+  int nzl = 0, z0 = 0, nyl = 0, ky0 = 0, nyb = 0, y0 = 0, kxl = 0, kx0 = 0, nxv = 0;
   long long N = 0;        // local voxels
   double Ntot = 0;        // global voxels
   int nphases = 0, nsmax = 0;
@@ -103,6 +112,8 @@ struct evp_solver {
     PeerMaps out_fwd{};              // forward y pass output: m[0] = local send layout, or one map per destination rank (p2p)
     PeerMaps out_inv{};              // inverse y pass output: m[0] = local plain layout
     cudaEvent_t ev_fwd = nullptr, ev_a1 = nullptr, ev_a2 = nullptr;
+    cudaEvent_t ev_p[4] = {nullptr, nullptr, nullptr, nullptr};   // pencil: kernel -> exchange hand-offs
+    cudaEvent_t ev_q[2] = {nullptr, nullptr};                     // pencil: row exchanges done (way back, forward)
   };
   int nchunks = 1, nzc = 0;
   Chunk ch[kMaxChunks];
@@ -114,6 +125,7 @@ struct evp_solver {
   cudaEvent_t ev_k4 = nullptr, ev_it0 = nullptr, ev_it1 = nullptr;
   bool green_inflight = false;       // forward FFT + Green + way-back exchange of the CURRENT stress already enqueued
   void *comm2 = nullptr;             // second communicator for the small all-reduces (compute stream)
+  void *comm_row = nullptr, *comm_col = nullptr;   // pencil: x<->y exchange among the py ranks of a row, y<->z among the pz of a column
   // peer-memory transport: the transposes are TMA stores into the other ranks' buffers (CUDA IPC mappings)
   bool p2p = false;
   double2 *WC = nullptr;             // p2p: receive buffer of the forward transpose (written by every rank's y pass)
@@ -128,6 +140,9 @@ struct evp_solver {
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
   evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100, 0, 0};
   long long ntwinned = 0;   // voxels reoriented by PTR so far (all ranks)
+  double facc = 0.0;        // F_acc: twin volume fraction accumulated over the history (all ranks; never decreases)
+  char *stage[2] = {nullptr, nullptr};   // pinned staging buffers of evp_get_field / evp_set_field / evp_set_microstructure
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int iudot[9]{}, iscau[6]{};
   double udot[9]{}, scau[6]{};
   bool strain_ctl[6]{};
@@ -227,15 +242,19 @@ int nccl_check(evp_handle h, int rc, const char *what) {
 }
 
 // all-to-all of equal contiguous pieces (FFT transpose): grouped ncclSend/ncclRecv
-int all_to_all(evp_handle h, const double2 *send, double2 *recv, cudaStream_t st) {
-  const size_t piece = (size_t)h->Lsplit.dstride * sizeof(double2);
+int all_to_all_on(evp_handle h, void *comm, int np, size_t piece_elems, const double2 *send, double2 *recv, cudaStream_t st) {
+  const size_t piece = piece_elems * sizeof(double2);
   int rc = g_nccl.GroupStart();
-  for (int p = 0; p < h->nranks && rc == 0; ++p) {
-    rc = g_nccl.Send((const char *)send + (size_t)p * piece, piece, kNcclChar, p, h->comm, st);
-    if (rc == 0) rc = g_nccl.Recv((char *)recv + (size_t)p * piece, piece, kNcclChar, p, h->comm, st);
+  for (int p = 0; p < np && rc == 0; ++p) {
+    rc = g_nccl.Send((const char *)send + (size_t)p * piece, piece, kNcclChar, p, comm, st);
+    if (rc == 0) rc = g_nccl.Recv((char *)recv + (size_t)p * piece, piece, kNcclChar, p, comm, st);
   }
   const int rc2 = g_nccl.GroupEnd();
   return nccl_check(h, rc ? rc : rc2, "nccl all-to-all");
+}
+// slab: y <-> z transpose among all ranks
+int all_to_all(evp_handle h, const double2 *send, double2 *recv, cudaStream_t st) {
+  return all_to_all_on(h, h->comm, h->nranks, (size_t)h->Lsplit.dstride, send, recv, st);
 }
 
 // kernel timers: event pairs around every launch, summed per kernel type in fetch_report
@@ -254,7 +273,7 @@ void tend(evp_handle h) {
 // K2 + K3 of chunk i, then (ranks > 1) its forward all-to-all on the communication stream
 int enqueue_forward_chunk(evp_handle h, int i, const double *field = nullptr) {
   evp_solver::Chunk &c = h->ch[i];
-  const int nrows = h->ny * h->nzc;
+  const int nrows = h->nyb * h->nzc;
   tbeg(h, 0, h->st);
   launch_xfwd(h->nx, field ? field : h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
   tend(h);
@@ -264,12 +283,12 @@ int enqueue_forward_chunk(evp_handle h, int i, const double *field = nullptr) {
     cudaEventRecord(c.ev_fwd, h->st);
     cudaStreamWaitEvent(h->stc, c.ev_fwd, 0);
     tbeg(h, 1, h->stc);
-    launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, true, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->stc);
+    launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, true, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->stc);
     tend(h);
     return EVP_OK;
   }
   tbeg(h, 1, h->st);
-  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxh, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
   tend(h);
   if (h->nranks > 1) {
     cudaEventRecord(c.ev_fwd, h->st);
@@ -300,7 +319,7 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
     cudaEventRecord(h->ev_b1, h->stc);
     cudaStreamWaitEvent(h->st, h->ev_b1, 0);
     tbeg(h, 2, h->st);
-    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
                   h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
     tend(h);
     tbeg(h, 6, h->st);
@@ -312,7 +331,7 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
   if (h->nranks > 1)
     for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
   tbeg(h, 2, h->st);
-  launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->nyl, h->ky0, h->nx,
+  launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
                 h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   tend(h);
   if (h->nranks > 1) {
@@ -335,13 +354,107 @@ int enqueue_back_chunk(evp_handle h, int i, bool plain = false) {
   evp_solver::Chunk &c = h->ch[i];
   if (h->nranks > 1 && !h->p2p) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
   tbeg(h, 3, h->st);
-  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxh, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
   tend(h);
   tbeg(h, 4, h->st);
   launch_xinv(h->nx, c.WB, plain ? nullptr : h->f.e, (plain || (h->flags & 2)) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase,
-              h->ny * h->nzc, h->Lplain, h->twx, h->st);
+              h->nyb * h->nzc, h->Lplain, h->twx, h->st);
   tend(h);
   return EVP_OK;
+}
+
+// ---- pencil decomposition (py x pz process grid, NCCL transport) ---------------------------------------------------------
+// Per z-chunk i the spectrum moves   K2 -> WA_i (x layout) -> [row a2a] -> WB_i -> K3 -> WA_i -> [column a2a] -> WB_i -> K4 in place
+//   -> [column a2a] -> WA_i -> K5 -> WB_i -> [row a2a] -> WA_i (x layout) -> K6.   Exchanges run on the communication stream.
+int pencil_row_a2a(evp_handle h, const double2 *send, double2 *recv) {
+  return all_to_all_on(h, h->comm_row, h->py, (size_t)h->Lplain.dstride, send, recv, h->stc);
+}
+int pencil_col_a2a(evp_handle h, const double2 *send, double2 *recv) {
+  return all_to_all_on(h, h->comm_col, h->pz, (size_t)h->Lsplit.dstride, send, recv, h->stc);
+}
+// K2 of chunk i + its row exchange
+int pencil_x_forward(evp_handle h, int i, const double *field) {
+  evp_solver::Chunk &c = h->ch[i];
+  tbeg(h, 0, h->st);
+  launch_xfwd(h->nx, field ? field : h->f.sig, c.WA, h->N, c.rowbase, h->nyb * h->nzc, h->Lplain, h->twx, h->st);
+  tend(h);
+  cudaEventRecord(c.ev_p[0], h->st);
+  cudaStreamWaitEvent(h->stc, c.ev_p[0], 0);
+  tbeg(h, 6, h->stc);
+  const int rc = pencil_row_a2a(h, c.WA, c.WB);
+  tend(h);
+  cudaEventRecord(c.ev_q[1], h->stc);
+  return rc;
+}
+// K3 of chunk i + its column exchange
+int pencil_y_forward(evp_handle h, int i) {
+  evp_solver::Chunk &c = h->ch[i];
+  cudaStreamWaitEvent(h->st, c.ev_q[1], 0);
+  tbeg(h, 1, h->st);
+  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
+  tend(h);
+  cudaEventRecord(c.ev_p[1], h->st);
+  cudaStreamWaitEvent(h->stc, c.ev_p[1], 0);
+  tbeg(h, 6, h->stc);
+  const int rc = pencil_col_a2a(h, c.WA, c.WB);
+  tend(h);
+  cudaEventRecord(c.ev_a1, h->stc);
+  return rc;
+}
+// K4 over all chunks, then the column exchange back per chunk
+int pencil_z_and_back(evp_handle h, int zmode) {
+  for (int i = 0; i < h->nchunks; ++i) cudaStreamWaitEvent(h->st, h->ch[i].ev_a1, 0);
+  tbeg(h, 2, h->st);
+  launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
+                h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  tend(h);
+  cudaEventRecord(h->ev_k4, h->st);
+  cudaStreamWaitEvent(h->stc, h->ev_k4, 0);
+  for (int i = 0; i < h->nchunks; ++i) {
+    tbeg(h, 6, h->stc);
+    const int rc = pencil_col_a2a(h, h->ch[i].WB, h->ch[i].WA);
+    tend(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ch[i].ev_a2, h->stc);
+  }
+  h->green_inflight = true;
+  return EVP_OK;
+}
+// K5 of chunk i + its row exchange back
+int pencil_y_back(evp_handle h, int i) {
+  evp_solver::Chunk &c = h->ch[i];
+  cudaStreamWaitEvent(h->st, c.ev_a2, 0);
+  tbeg(h, 3, h->st);
+  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
+  tend(h);
+  cudaEventRecord(c.ev_p[2], h->st);
+  cudaStreamWaitEvent(h->stc, c.ev_p[2], 0);
+  tbeg(h, 6, h->stc);
+  const int rc = pencil_row_a2a(h, c.WB, c.WA);
+  tend(h);
+  cudaEventRecord(c.ev_q[0], h->stc);
+  return rc;
+}
+// K6 of chunk i
+void pencil_x_back(evp_handle h, int i, bool plain) {
+  evp_solver::Chunk &c = h->ch[i];
+  cudaStreamWaitEvent(h->st, c.ev_q[0], 0);
+  tbeg(h, 4, h->st);
+  launch_xinv(h->nx, c.WA, plain ? nullptr : h->f.e, (plain || (h->flags & 2)) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase,
+              h->nyb * h->nzc, h->Lplain, h->twx, h->st);
+  tend(h);
+}
+int pencil_forward_all(evp_handle h, const double *field, int zmode) {
+  int rc = EVP_OK;
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = pencil_x_forward(h, i, field);
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = pencil_y_forward(h, i);
+  return rc ? rc : pencil_z_and_back(h, zmode);
+}
+int pencil_back_all(evp_handle h, bool plain) {
+  int rc = EVP_OK;
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = pencil_y_back(h, i);
+  for (int i = 0; i < h->nchunks && rc == 0; ++i) pencil_x_back(h, i, plain);
+  return rc;
 }
 
 void enqueue_const_chunk(evp_handle h, int i) {
@@ -355,8 +468,8 @@ int enqueue_reduce_macro(evp_handle h) {
   launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals, h->st);
   if (h->nranks > 1) {
     void *cm = h->comm2 ? h->comm2 : h->comm;
-    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 10, kNcclDouble, kNcclSum, cm, h->st);
-    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 10, h->d_totals + 10, 1, kNcclDouble, kNcclMax, cm, h->st);
+    int rc = g_nccl.AllReduce(h->d_totals, h->d_totals, 11, kNcclDouble, kNcclSum, cm, h->st);
+    if (rc == 0) rc = g_nccl.AllReduce(h->d_totals + 11, h->d_totals + 11, 1, kNcclDouble, kNcclMax, cm, h->st);
     if (rc) return nccl_check(h, rc, "nccl allreduce");
   }
   launch_macro(h->d_totals, h->d_macro, h->Ntot, h->st);
@@ -370,6 +483,7 @@ void invalidate_green(evp_handle h) {
 }
 
 int enqueue_forward_all(evp_handle h, const double *field = nullptr, int zmode = 0) {
+  if (h->py > 1) return pencil_forward_all(h, field, zmode);
   for (int i = 0; i < h->nchunks; ++i) {
     int rc = enqueue_forward_chunk(h, i, field);
     if (rc) return rc;
@@ -381,7 +495,8 @@ int enqueue_forward_all(evp_handle h, const double *field = nullptr, int zmode =
 int enqueue_rotation_field(evp_handle h) {
   invalidate_green(h);   // the chain reuses the spectral buffers
   int rc = enqueue_forward_all(h, h->f.e, 2);
-  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i, true);
+  if (h->py > 1) { if (rc == 0) rc = pencil_back_all(h, true); }
+  else for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i, true);
   h->green_inflight = false;
   return rc;
 }
@@ -390,7 +505,8 @@ int enqueue_rotation_field(evp_handle h) {
 int enqueue_green(evp_handle h) {
   int rc = EVP_OK;
   if (!h->green_inflight) rc = enqueue_forward_all(h);
-  for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i);
+  if (h->py > 1) { if (rc == 0) rc = pencil_back_all(h, false); }
+  else for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = enqueue_back_chunk(h, i);
   h->green_inflight = false;
   return rc;
 }
@@ -408,6 +524,20 @@ int enqueue_iteration(evp_handle h) {
   int rc = EVP_OK;
   if ((h->flags & 1) && h->tm.made) { h->tm.n = 0; cudaEventRecord(h->ev_it0, h->st); }
   if (!h->green_inflight) rc = enqueue_forward_all(h);
+  if (h->py > 1) {
+    // pencils: the row exchange of chunk i runs under K5 / K6 / K1 / K2 of its neighbours, the column exchange under K3
+    for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = pencil_y_back(h, i);
+    for (int i = 0; i < h->nchunks && rc == 0; ++i) {
+      pencil_x_back(h, i, false);
+      enqueue_const_chunk(h, i);
+      rc = pencil_x_forward(h, i, nullptr);
+    }
+    if (rc == 0) rc = enqueue_reduce_macro(h);
+    for (int i = 0; i < h->nchunks && rc == 0; ++i) rc = pencil_y_forward(h, i);
+    if (rc == 0) rc = pencil_z_and_back(h, 0);
+    if ((h->flags & 1) && h->tm.made) cudaEventRecord(h->ev_it1, h->st);
+    return rc;
+  }
   for (int i = 0; i < h->nchunks && rc == 0; ++i) {
     rc = enqueue_back_chunk(h, i);
     if (rc) break;
@@ -431,8 +561,9 @@ int fetch_report(evp_handle h, evp_iter_report *rep) {
     rep->err_stress = m.err_s;
     rep->err_strain = m.err_e;
     for (int c = 0; c < 6; ++c) { rep->savg[c] = m.savg[c]; rep->emacro[c] = m.E[c]; }
-    rep->converged = (m.iter >= h->ctrl.itmin && m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
+    rep->converged = (m.iter >= h->ctrl.itmin && m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain && m.unconverged == 0) ? 1 : 0;
     rep->nonfinite = m.nonfinite;
+    rep->unconverged = m.unconverged;
   }
   if ((h->flags & 1) && h->tm.made) {
     if (h->stc) cudaStreamSynchronize(h->stc);
@@ -443,6 +574,81 @@ int fetch_report(evp_handle h, evp_iter_report *rep) {
     if (cudaEventElapsedTime(&ms, h->ev_it0, h->ev_it1) == cudaSuccess) h->last_ms[7] = ms;
   }
   return m.nonfinite ? fail(h, EVP_ERR_NUMERIC, "Newton produced a non-finite value / bad pivot") : EVP_OK;
+}
+
+// ---- host <-> device field transfers through pinned staging --------------------------------------------------------------
+// Caller buffers are pageable; a plain cudaMemcpy of pageable memory runs at ~5 GB/s on these hosts (single-threaded driver
+// staging).  Here: two pinned buffers, host-side copies split over a few threads, DMA of one buffer under the host copy of the
+// other.  (std::thread, not OpenMP: torchrun exports OMP_NUM_THREADS=1.)
+constexpr size_t kStageBytes = (size_t)32 << 20;
+int stage_threads() {
+  static int n = 0;
+  if (!n) {
+    const unsigned hc = std::thread::hardware_concurrency();
+    n = (int)std::max(1u, std::min(8u, hc ? hc : 4u));
+    if (const char *e = getenv("EVP_STAGE_THREADS")) n = std::max(1, atoi(e));
+  }
+  return n;
+}
+void par_copy(char *dst, const char *src, size_t n) {
+  const int nt = (n < ((size_t)4 << 20)) ? 1 : stage_threads();
+  if (nt == 1) { std::memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+  for (int t = 0; t < nt; ++t) {
+    const size_t a = (size_t)t * per, b = std::min(n, a + per);
+    if (a >= b) break;
+    th.emplace_back([=]() { std::memcpy(dst + a, src + a, b - a); });
+  }
+  for (auto &t : th) t.join();
+}
+int stage_init(evp_handle h) {
+  for (int b = 0; b < 2; ++b) {
+    if (!h->stage[b]) CUDA_OK(h, cudaMallocHost(&h->stage[b], kStageBytes));
+    if (!h->stage_ev[b]) CUDA_OK(h, cudaEventCreateWithFlags(&h->stage_ev[b], cudaEventDisableTiming));
+  }
+  return EVP_OK;
+}
+// enqueues on h->st; the caller synchronises the stream
+int copy_h2d(evp_handle h, void *dst, const void *src, size_t bytes) {
+  if (bytes < ((size_t)1 << 20)) { CUDA_OK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st)); return EVP_OK; }
+  int rc = stage_init(h);
+  if (rc) return rc;
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += kStageBytes, ++k) {
+    const int b = k & 1;
+    const size_t n = std::min(kStageBytes, bytes - off);
+    CUDA_OK(h, cudaEventSynchronize(h->stage_ev[b]));   // the DMA that last read this buffer is done
+    par_copy(h->stage[b], (const char *)src + off, n);
+    CUDA_OK(h, cudaMemcpyAsync((char *)dst + off, h->stage[b], n, cudaMemcpyHostToDevice, h->st));
+    CUDA_OK(h, cudaEventRecord(h->stage_ev[b], h->st));
+  }
+  return EVP_OK;
+}
+// complete on return
+int copy_d2h(evp_handle h, void *dst, const void *src, size_t bytes) {
+  if (bytes < ((size_t)1 << 20)) {
+    CUDA_OK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
+    CUDA_OK(h, cudaStreamSynchronize(h->st));
+    return EVP_OK;
+  }
+  int rc = stage_init(h);
+  if (rc) return rc;
+  const size_t nchunk = (bytes + kStageBytes - 1) / kStageBytes;
+  auto issue = [&](size_t k) -> cudaError_t {
+    const size_t off = k * kStageBytes, n = std::min(kStageBytes, bytes - off);
+    cudaError_t e = cudaMemcpyAsync(h->stage[k & 1], (const char *)src + off, n, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaEventRecord(h->stage_ev[k & 1], h->st);
+    return e;
+  };
+  CUDA_OK(h, issue(0));
+  for (size_t k = 0; k < nchunk; ++k) {
+    if (k + 1 < nchunk) CUDA_OK(h, issue(k + 1));     // the other buffer was copied out in the previous round
+    CUDA_OK(h, cudaEventSynchronize(h->stage_ev[k & 1]));
+    const size_t off = k * kStageBytes, n = std::min(kStageBytes, bytes - off);
+    par_copy((char *)dst + off, h->stage[k & 1], n);
+  }
+  return EVP_OK;
 }
 
 evp_handle g_active = nullptr;  // handle whose tables currently sit in __constant__ memory
@@ -501,7 +707,12 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, EVP_ERR_ARG, "evp_create: bad rank/nranks");
   if (!fft_size_supported(grid->nx) || !fft_size_supported(grid->ny) || !fft_size_supported(grid->nz))
     return fail(nullptr, EVP_ERR_UNSUPPORTED, "grid sizes must be powers of two in [8, 1024]");
-  if (grid->nz % nranks || grid->ny % nranks) return fail(nullptr, EVP_ERR_UNSUPPORTED, "ny and nz must be divisible by nranks");
+  const int py = (dist && dist->py > 1) ? dist->py : 1;
+  if (nranks % py) return fail(nullptr, EVP_ERR_ARG, "evp_create: py must divide nranks");
+  const int pz = nranks / py;
+  if (grid->nz % pz || grid->ny % pz || grid->ny % py) return fail(nullptr, EVP_ERR_UNSUPPORTED, "ny must be divisible by py and pz, nz by pz");
+  if (g_device >= 0 && g_device != device)
+    return fail(nullptr, EVP_ERR_UNSUPPORTED, "this process already drives CUDA device " + std::to_string(g_device) + ": one GPU per process (see evpfft.h)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
     return fail(nullptr, EVP_ERR_DEVICE, "no CUDA device: this library has no CPU fallback");
@@ -509,6 +720,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, EVP_ERR_DEVICE, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(nullptr, EVP_ERR_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", library is built for sm_100a only");
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EVP_ERR_DEVICE, "cudaSetDevice failed");
+  g_device = device;
 
   evp_solver *S = new evp_solver();
   evp_handle h = S;
@@ -518,11 +730,16 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   if (!(S->g.dz > 0)) S->g.dz = 1.0;
   S->nx = grid->nx; S->ny = grid->ny; S->nz = grid->nz;
   S->nxh = S->nx / 2 + 1;
-  S->nxp = (S->nxh + 7) / 8 * 8;
   S->nranks = nranks; S->rank = rank; S->device = device;
-  S->nzl = S->nz / nranks; S->z0 = rank * S->nzl;
-  S->nyl = S->ny / nranks; S->ky0 = rank * S->nyl;
-  S->N = (long long)S->nx * S->ny * S->nzl;
+  S->py = py; S->pz = pz; S->iy = rank / pz; S->iz = rank % pz;
+  S->kxl = ((S->nxh + py - 1) / py + 7) / 8 * 8;          // kx columns per row rank (pitch of every spectral row)
+  S->nxp = S->kxl;
+  S->kx0 = S->iy * S->kxl;
+  S->nxv = std::max(0, std::min(S->kxl, S->nxh - S->kx0));
+  S->nzl = S->nz / pz; S->z0 = S->iz * S->nzl;
+  S->nyl = S->ny / pz; S->ky0 = S->iz * S->nyl;
+  S->nyb = S->ny / py; S->y0 = S->iy * S->nyb;
+  S->N = (long long)S->nx * S->nyb * S->nzl;
   S->Ntot = (double)S->nx * S->ny * S->nz;
   S->nphases = nphases;
   S->ph.assign(phases, phases + nphases);
@@ -591,12 +808,23 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
     if (rc) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "ncclCommInitRank failed"); }
     // separate communicator for the tiny norm all-reduces so that they do not queue behind the transposes
     if (g_nccl.CommSplit && g_nccl.CommSplit(S->comm, 0, rank, &S->comm2, nullptr) != 0) S->comm2 = nullptr;
+    if (py > 1) {
+      if (!g_nccl.CommSplit || g_nccl.CommSplit(S->comm, S->iz, S->iy, &S->comm_row, nullptr) != 0 ||
+          g_nccl.CommSplit(S->comm, S->iy, S->iz, &S->comm_col, nullptr) != 0) {
+        evp_destroy(S);
+        return fail(nullptr, EVP_ERR_DEVICE, "ncclCommSplit (pencil row / column communicators) failed");
+      }
+    }
   }
-  // transport of the FFT transposes: 0/auto = peer-memory TMA stores when CUDA IPC works, 1 = NCCL all-to-all, 2 = p2p required
+  // transport of the FFT transposes (evp_transport_kind); pencils exchange through NCCL only
   if (nranks > 1) {
     int tr = dist->transport;
-    if (const char *e = getenv("EVP_TRANSPORT")) tr = (std::string(e) == "nccl") ? 1 : (std::string(e) == "p2p" ? 2 : tr);
-    if (tr != 1) {
+    if (const char *e = getenv("EVP_TRANSPORT")) tr = (std::string(e) == "nccl") ? EVP_TRANSPORT_NCCL : (std::string(e) == "p2p" ? EVP_TRANSPORT_P2P : tr);
+    if (py > 1) {
+      if (tr == EVP_TRANSPORT_P2P) { evp_destroy(S); return fail(nullptr, EVP_ERR_UNSUPPORTED, "pencil decomposition supports the NCCL transport only"); }
+      tr = EVP_TRANSPORT_NCCL;
+    }
+    if (tr != EVP_TRANSPORT_NCCL) {
       std::string why;
       if (nranks > kMaxRanks) why = "too many ranks";
       if (why.empty() && cudaMalloc(&S->WC, wbytes) != cudaSuccess) why = "cudaMalloc(WC) failed";
@@ -637,7 +865,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
         S->p2p = (flag == 0.0);
         if (!S->p2p && why.empty()) why = "a peer could not map the buffers";
       }
-      if (!S->p2p && tr == 2) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "peer-memory transport requested but unavailable: " + why); }
+      if (!S->p2p && tr == EVP_TRANSPORT_P2P) { evp_destroy(S); return fail(nullptr, EVP_ERR_DEVICE, "peer-memory transport requested but unavailable: " + why); }
     }
     CK(cudaMalloc(&S->d_bar, sizeof(double)));
     CK(cudaMemset(S->d_bar, 0, sizeof(double)));
@@ -647,41 +875,45 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   {
     int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? 4 : 1);   // env: also on one rank (tests)
     want = std::max(1, std::min(want, (int)(S->p2p ? kMaxChunksP2P : kMaxChunks)));
-    while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->ny * S->nx) % 128 != 0)) want /= 2;
+    while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->nyb * S->nx) % 128 != 0)) want /= 2;
     S->nchunks = want;
     S->nzc = S->nzl / want;
   }
-  S->Lplain.nyl = S->ny; S->Lplain.nzl = S->nzc; S->Lplain.nxp = S->nxp; S->Lplain.nxh = S->nxh;
-  S->Lplain.zstride = (long long)S->ny * S->nxp;
+  // "plain" = the x-side view of the y stage: rows grouped by the row rank that owns them in real space (py groups of nyb
+  // rows; one group of ny rows for slabs);  "split" = its z-side view: rows grouped by the column rank that transforms them
+  S->Lplain.nyl = S->nyb; S->Lplain.nzl = S->nzc; S->Lplain.nxp = S->nxp; S->Lplain.nxh = S->nxh;
+  S->Lplain.zstride = (long long)S->nyb * S->nxp;
   S->Lplain.cstride = (long long)S->nzc * S->Lplain.zstride;
   S->Lplain.dstride = 6 * S->Lplain.cstride;
   S->Lsplit.nyl = S->nyl; S->Lsplit.nzl = S->nzc; S->Lsplit.nxp = S->nxp; S->Lsplit.nxh = S->nxh;
   S->Lsplit.zstride = (long long)S->nyl * S->nxp;
   S->Lsplit.cstride = (long long)S->nzc * S->Lsplit.zstride;
   S->Lsplit.dstride = 6 * S->Lsplit.cstride;
-  S->Lplain.lg_nyl = ilog2i(S->ny); S->Lplain.lg_nzl = ilog2i(S->nzc);
+  S->Lplain.lg_nyl = ilog2i(S->nyb); S->Lplain.lg_nzl = ilog2i(S->nzc);
   S->Lsplit.lg_nyl = ilog2i(S->nyl); S->Lsplit.lg_nzl = ilog2i(S->nzc);
   S->lg_nzl = ilog2i(S->nzl); S->lg_nzc = ilog2i(S->nzc);
   {
     std::string e;
-    const int ycp = std::min(S->ny, 256), ycs = std::min(S->nyl, 256);
+    const int ycp = std::min(S->nyb, 256), ycs = std::min(S->nyl, 256);
     S->zrun = std::min(S->nzc, 256);
     S->ti_y_plain = {S->Lplain.lg_nyl, ycp};
     S->ti_y_split = {S->Lsplit.lg_nyl, ycs};
-    const size_t csize = (size_t)6 * S->nzc * S->ny * S->nxp;   // complex elements per chunk sub-buffer
+    const size_t csize = (size_t)6 * S->nzc * S->ny * S->nxp;   // complex elements per chunk sub-buffer (same in the x, y and z stages)
     for (int i = 0; i < S->nchunks; ++i) {
       evp_solver::Chunk &c = S->ch[i];
-      c.rowbase = i * S->nzc * S->ny;
+      c.rowbase = i * S->nzc * S->nyb;
       c.vbase = (long long)c.rowbase * S->nx;
-      c.count = (long long)S->nzc * S->ny * S->nx;
+      c.count = (long long)S->nzc * S->nyb * S->nx;
       c.WA = S->WA + (size_t)i * csize;
       c.WB = S->WB + (size_t)i * csize;
       // K2 -> WB (plain) -> K3 -> WA (split) -> [all-to-all -> WB] -> K4 in place -> [all-to-all -> WA] -> K5 -> WB (plain) -> K6
       // p2p:  K2 -> WB (plain) -> K3 stores into every peer's WC -> K4 reads WC, stores into every peer's WA -> K5 -> WB -> K6
       double2 *Wz = S->p2p ? S->WC + (size_t)i * csize : ((nranks > 1) ? c.WB : c.WA);
-      bool ok = make_tmap(&c.tm_y_plain, c.WB, S->Lplain, 1, ypass_tx(), ycp, 1, &e) &&
-                make_tmap(&c.tm_y_split, c.WA, S->Lsplit, nranks, ypass_tx(), ycs, 1, &e) &&
-                make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, nranks, zpass_tx(S->nz), 1, S->zrun, &e);
+      // pencil (NCCL): K2 -> WA (x layout) -> [row a2a -> WB] -> K3 -> WA (split) -> [column a2a -> WB] -> K4 in place -> [column a2a -> WA]
+      //                -> K5 -> WB (plain) -> [row a2a -> WA (x layout)] -> K6
+      bool ok = make_tmap(&c.tm_y_plain, c.WB, S->Lplain, py, ypass_tx(), ycp, 1, &e) &&
+                make_tmap(&c.tm_y_split, c.WA, S->Lsplit, pz, ypass_tx(), ycs, 1, &e) &&
+                make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, pz, zpass_tx(S->nz), 1, S->zrun, &e);
       for (int p = 0; p < kMaxRanks && ok; ++p) {
         c.out_inv.m[p] = c.tm_y_plain;
         c.out_fwd.m[p] = c.tm_y_split;
@@ -701,6 +933,8 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
         CK(cudaEventCreateWithFlags(&c.ev_fwd, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_a1, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_a2, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : c.ev_p) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : c.ev_q) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       }
     }
     for (int i = S->nchunks; i < kMaxChunks; ++i) S->zmaps.m[i] = S->zmaps.m[0];
@@ -748,7 +982,13 @@ int evp_destroy(evp_handle h) {
   }
   cudaFree(h->WC); cudaFree(h->d_bar);
   if (h->ev_b1) cudaEventDestroy(h->ev_b1);
+  if (h->comm_row && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_row);
+  if (h->comm_col && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_col);
   if (h->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm2);
+  for (int b = 0; b < 2; ++b) {
+    if (h->stage[b]) cudaFreeHost(h->stage[b]);
+    if (h->stage_ev[b]) cudaEventDestroy(h->stage_ev[b]);
+  }
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->f.sig); cudaFree(h->f.e); cudaFree(h->f.epsp); cudaFree(h->f.edotp); cudaFree(h->f.crss);
   cudaFree(h->f.mrot); cudaFree(h->f.jb); cudaFree(h->f.itc); cudaFree(h->f.orient); cudaFree(h->f.orient_rep);
@@ -764,6 +1004,8 @@ int evp_destroy(evp_handle h) {
     if (h->ch[i].ev_fwd) cudaEventDestroy(h->ch[i].ev_fwd);
     if (h->ch[i].ev_a1) cudaEventDestroy(h->ch[i].ev_a1);
     if (h->ch[i].ev_a2) cudaEventDestroy(h->ch[i].ev_a2);
+    for (cudaEvent_t ev : h->ch[i].ev_p) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ch[i].ev_q) if (ev) cudaEventDestroy(ev);
   }
   if (h->ev_k4) cudaEventDestroy(h->ev_k4);
   if (h->ev_it0) cudaEventDestroy(h->ev_it0);
@@ -780,8 +1022,26 @@ int evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl) {
   if (nzl) *nzl = h->nzl;
   return EVP_OK;
 }
+int evp_local_block(evp_handle h, int32_t *y0, int32_t *nyl, int32_t *z0, int32_t *nzl) {
+  if (!h) return EVP_ERR_ARG;
+  if (y0) *y0 = h->y0;
+  if (nyl) *nyl = h->nyb;
+  if (z0) *z0 = h->z0;
+  if (nzl) *nzl = h->nzl;
+  return EVP_OK;
+}
 int evp_nsys_max(evp_handle h) { return h ? h->nsmax : EVP_ERR_ARG; }
-int evp_transport(evp_handle h) { return (h && h->p2p) ? 1 : 0; }
+int evp_transport(evp_handle h) { return (h && h->p2p) ? EVP_TRANSPORT_P2P : EVP_TRANSPORT_NCCL; }
+const char *evp_build_id(void) { return EVP_SRC_HASH; }
+int64_t evp_launch_count(evp_handle) { return (int64_t)launch_count(); }
+int evp_debug_fp64_peak(evp_handle h, int32_t reps, double *tflops) {
+  if (!h || !tflops) return EVP_ERR_ARG;
+  cudaSetDevice(h->device);
+  CUDA_OK(h, cudaStreamSynchronize(h->st));
+  *tflops = measure_fp64_peak(reps, h->st);
+  CUDA_OK(h, cudaGetLastError());
+  return (*tflops > 0.0) ? EVP_OK : fail(h, EVP_ERR_DEVICE, "fp64 peak measurement failed");
+}
 void *evp_stream(evp_handle h) { return h ? (void *)h->st : nullptr; }
 
 int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *phase, const double *rot9) {
@@ -806,6 +1066,9 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
       for (long long v = 0; v < N && ok; ++v) {
         long long &r = rep[grain[v]];
         if (r < 0) { r = v; continue; }
+        // the class tables (Jb = S0_c + S_c, M) are built from the representative voxel: every voxel of the class must
+        // share its rotation AND its phase (a grain id that spans two phases falls back to per-voxel classes)
+        if (phase && phase[v] != phase[r]) { ok = false; break; }
         for (int k = 0; k < 9; ++k)
           if (rot9[(size_t)k * N + v] != rot9[(size_t)k * N + r]) { ok = false; break; }
       }
@@ -828,12 +1091,13 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
       h->f.norient = NO;
     }
     CUDA_OK(h, cudaMemcpy(h->f.orient_rep, rep.data(), sizeof(long long) * NO, cudaMemcpyHostToDevice));
-    CUDA_OK(h, cudaMemcpy(h->f.orient, ok ? grain : oid.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+    { int rc = copy_h2d(h, h->f.orient, ok ? grain : oid.data(), sizeof(int32_t) * N); if (rc) return rc; }
+    CUDA_OK(h, cudaStreamSynchronize(h->st));   // oid is a local
   }
-  CUDA_OK(h, cudaMemcpyAsync(h->f.grain, grain, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
-  if (phase) CUDA_OK(h, cudaMemcpyAsync(h->f.phase, phase, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->st));
+  { int rc = copy_h2d(h, h->f.grain, grain, sizeof(int32_t) * N); if (rc) return rc; }
+  if (phase) { int rc = copy_h2d(h, h->f.phase, phase, sizeof(int32_t) * N); if (rc) return rc; }
   else CUDA_OK(h, cudaMemsetAsync(h->f.phase, 0, sizeof(int32_t) * N, h->st));
-  CUDA_OK(h, cudaMemcpyAsync(h->f.rot, rot9, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, h->st));
+  { int rc = copy_h2d(h, h->f.rot, rot9, sizeof(double) * 9 * N); if (rc) return rc; }
   CUDA_OK(h, cudaMemsetAsync(h->f.sig, 0, sizeof(double) * 6 * N, h->st));
   CUDA_OK(h, cudaMemsetAsync(h->f.e, 0, sizeof(double) * 6 * N, h->st));
   CUDA_OK(h, cudaMemsetAsync(h->f.epsp, 0, sizeof(double) * 6 * N, h->st));
@@ -842,6 +1106,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   CUDA_OK(h, cudaMemsetAsync(h->f.wrot, 0, sizeof(double) * 3 * N, h->st));
   CUDA_OK(h, cudaMemsetAsync(h->f.twinned, 0, sizeof(int32_t) * N, h->st));
   h->ntwinned = 0;
+  h->facc = 0.0;
   if (h->f.twinf) CUDA_OK(h, cudaMemsetAsync(h->f.twinf, 0, sizeof(double) * std::max(h->nsmax, 1) * N, h->st));
   if (h->f.de) CUDA_OK(h, cudaMemsetAsync(h->f.de, 0, sizeof(double) * 6 * N, h->st));
   activate(h);
@@ -851,6 +1116,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
     for (int c = 0; c < 6; ++c) { m.E[c] = m.Et[c] = m.dEpend[c] = m.savg[c] = m.epavg[c] = 0.0; h->Et[c] = 0; h->Edot_prev[c] = 0; }
     m.err_s = m.err_e = m.newton_mean = 0.0;
     m.newton_max = m.nonfinite = m.iter = 0;
+    m.unconverged = 0;
     CUDA_OK(h, cudaMemcpyAsync(h->d_macro, &m, sizeof(MacroDev), cudaMemcpyHostToDevice, h->st));
   }
   CUDA_OK(h, cudaStreamSynchronize(h->st));
@@ -1070,15 +1336,18 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   launch_commit(h->f, h->nsmax, h->dt, wapp, tex, twn, h->d_partials, h->st);
   launch_reduce(h->d_partials, h->N, h->d_scratch, h->d_totals + 16, h->st);
   if (h->nranks > 1) {
-    int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 10, kNcclDouble, kNcclSum, h->comm2 ? h->comm2 : h->comm, h->st);
+    int rc = g_nccl.AllReduce(h->d_totals + 16, h->d_totals + 16, 11, kNcclDouble, kNcclSum, h->comm2 ? h->comm2 : h->comm, h->st);
     if (rc) return nccl_check(h, rc, "nccl allreduce (commit)");
   }
-  double tot[11];
+  double tot[12];
   CUDA_OK(h, cudaMemcpyAsync(tot, h->d_totals + 16, sizeof(tot), cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaMemcpyAsync(h->h_macro, h->d_macro, sizeof(MacroDev), cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));
   CUDA_OK(h, cudaGetLastError());
-  const double Facc = tot[0] / h->Ntot;
+  // F_acc is a history sum (Tome, Lebensohn, Kocks 1991): this increment's twin fraction is added, nothing is ever
+  // subtracted when a voxel reorients and its per-system fractions are reset
+  if (twn) h->facc += tot[1] / h->Ntot;
+  const double Facc = h->facc;
   long long nre = 0;
   if (twn) {
     const double Feff = (double)h->ntwinned / h->Ntot;
@@ -1114,7 +1383,7 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (rep) {
     rep->iters = m.iter;
     rep->err_stress = m.err_s; rep->err_strain = m.err_e;
-    rep->converged = (m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain) ? 1 : 0;
+    rep->converged = (m.err_s <= h->ctrl.tol_stress && m.err_e <= h->ctrl.tol_strain && m.unconverged == 0) ? 1 : 0;
     for (int c = 0; c < 6; ++c) { rep->savg[c] = m.savg[c]; rep->emacro[c] = m.E[c]; rep->epavg[c] = tot[2 + c] / h->Ntot; }
     rep->twin_acc = Facc; rep->twin_eff = (double)h->ntwinned / h->Ntot; rep->reoriented = nre;
   }
@@ -1150,9 +1419,7 @@ int evp_get_field(evp_handle h, evp_field f, void *host, size_t bytes) {
     std::memset(host, 0, need);
     return EVP_OK;
   }
-  CUDA_OK(h, cudaMemcpyAsync(host, p, need, cudaMemcpyDeviceToHost, h->st));
-  CUDA_OK(h, cudaStreamSynchronize(h->st));
-  return EVP_OK;
+  return copy_d2h(h, host, p, need);
 }
 
 int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
@@ -1164,7 +1431,7 @@ int evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes) {
   if (field_comps(h, f) == 0) return fail(h, EVP_ERR_ARG, "unknown field");
   if (bytes != need) return fail(h, EVP_ERR_ARG, "set_field: size mismatch");
   if (!p) return fail(h, EVP_ERR_STATE, "field is not allocated in this configuration");
-  CUDA_OK(h, cudaMemcpyAsync(p, host, need, cudaMemcpyHostToDevice, h->st));
+  { int rc = copy_h2d(h, p, host, need); if (rc) return rc; }
   if (f == EVP_FIELD_ROTATION) {
     int rc = switch_to_voxel_classes(h);
     if (rc) return rc;
@@ -1187,11 +1454,13 @@ int evp_get_macro(evp_handle h, double emacro[6], double savg[6]) {
 }
 
 
+// Restart file format "EVPCKPT2" (shared with oracle/evp_oracle.cpp; documented in include/evpfft.h)
 struct CkptHeader {
   char magic[8];
-  int32_t nx, ny, nz, z0, nzl, nsmax, nranks, rank;
+  int32_t nx, ny, nz, y0, nyl, z0, nzl, nsmax, nranks, rank;
   double Et[6], Edot_prev[6];
   int64_t ntwinned;
+  double facc;
 };
 
 static int ckpt_io(evp_handle h, std::FILE *f, bool write) {
@@ -1226,10 +1495,12 @@ int evp_save_state(evp_handle h, const char *path) {
   std::FILE *f = std::fopen(path, "wb");
   if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot write ") + path);
   CkptHeader hd{};
-  std::memcpy(hd.magic, "EVPCKPT1", 8);
-  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.z0 = h->z0; hd.nzl = h->nzl; hd.nsmax = h->nsmax; hd.nranks = h->nranks; hd.rank = h->rank;
+  std::memcpy(hd.magic, "EVPCKPT2", 8);
+  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.y0 = h->y0; hd.nyl = h->nyb; hd.z0 = h->z0; hd.nzl = h->nzl; hd.nsmax = h->nsmax;
+  hd.nranks = h->nranks; hd.rank = h->rank;
   for (int c = 0; c < 6; ++c) { hd.Et[c] = h->Et[c]; hd.Edot_prev[c] = h->Edot_prev[c]; }
   hd.ntwinned = h->ntwinned;
+  hd.facc = h->facc;
   int rc = (std::fwrite(&hd, sizeof(hd), 1, f) == 1) ? EVP_OK : fail(h, EVP_ERR_ARG, "short write");
   if (rc == EVP_OK) rc = ckpt_io(h, f, true);
   std::fclose(f);
@@ -1245,9 +1516,19 @@ int evp_load_state(evp_handle h, const char *path) {
   std::FILE *f = std::fopen(path, "rb");
   if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot read ") + path);
   CkptHeader hd{};
-  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT1", 8) == 0;
-  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nzl || hd.z0 != h->z0 || hd.nsmax != h->nsmax)) ok = false;
+  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT2", 8) == 0;
+  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nzl || hd.z0 != h->z0 || hd.nyl != h->nyb || hd.y0 != h->y0 ||
+             hd.nsmax != h->nsmax)) ok = false;
   if (!ok) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint does not match this handle"); }
+  {
+    // the whole payload must be there before any device field is overwritten (a truncated file leaves the state untouched)
+    const size_t N = (size_t)h->N, ns = (size_t)std::max(h->nsmax, 1);
+    const size_t need = sizeof(hd) + (size_t)8 * N * (6 + 6 + 6 + ns + 9 + 1 + ns + 3) + (size_t)4 * N * 3;
+    std::fseek(f, 0, SEEK_END);
+    const long have = std::ftell(f);
+    std::fseek(f, (long)sizeof(hd), SEEK_SET);
+    if (have < 0 || (size_t)have != need) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint file is truncated or has trailing bytes"); }
+  }
   int rc = ckpt_io(h, f, false);
   std::fclose(f);
   if (rc) return rc;
@@ -1257,6 +1538,7 @@ int evp_load_state(evp_handle h, const char *path) {
     m.E[c] = m.Et[c] = hd.Et[c]; m.dEpend[c] = 0.0;
   }
   h->ntwinned = hd.ntwinned;
+  h->facc = hd.facc;
   CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));
   rc = switch_to_voxel_classes(h);   // orientations may be anything now
   if (rc) return rc;
@@ -1272,7 +1554,7 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   invalidate_green(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
   launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].out_inv, false, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
-  launch_zfused(h->nz, 1, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+  launch_zfused(h->nz, 1, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, 0, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

@@ -1,7 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, z-slab decomposition.
+"""Multi-GPU plumbing: one process per GPU, z-slab or pencil decomposition.
 
-torch.distributed is used only as plumbing (rendezvous + broadcasting the NCCL unique id); the FFT
-transposes are grouped ncclSend/ncclRecv all-to-alls issued by the C library itself on its stream.
+torch.distributed is used only as plumbing (rendezvous + broadcasting the NCCL unique id).  The FFT transposes are
+done by the C library itself: by default (slabs) as TMA stores into the other ranks' buffers (CUDA IPC over NVLink)
+fused into the y and z FFT kernels, or - evp_dist.transport = EVP_TRANSPORT_NCCL, EVP_TRANSPORT=nccl, pencils, or
+when IPC mapping fails - as grouped ncclSend/ncclRecv all-to-alls on its communication stream.
 The index helpers below restate the spectral-buffer layouts of lapx_b200/csrc/kernels.cuh
 (SpecLayout) in numpy so that the decomposition logic can be tested on CPU with the gloo backend."""
 from __future__ import annotations
@@ -58,8 +60,9 @@ def nccl_unique_id(lib, rank: int, broadcast_bytes) -> "C.Array":
     return (C.c_uint8 * 128)(*[int(v) for v in arr])
 
 
-def make_dist(lib, world: int, rank: int, device: int, td=None) -> api.Dist | None:
-    """Build the evp_dist argument; `td` is an initialised torch.distributed module (any backend)."""
+def make_dist(lib, world: int, rank: int, device: int, td=None, transport: int = api.TRANSPORT_AUTO, py: int = 1) -> api.Dist | None:
+    """Build the evp_dist argument; `td` is an initialised torch.distributed module (any backend).
+    py >= 2 selects the pencil decomposition on a py x (world/py) process grid."""
     if world == 1:
         return None
     import torch
@@ -73,4 +76,4 @@ def make_dist(lib, world: int, rank: int, device: int, td=None) -> api.Dist | No
         return t.cpu().numpy()
 
     uid = nccl_unique_id(lib, rank, bcast)
-    return api.Dist(world, rank, device, 0, uid)
+    return api.Dist(world, rank, device, int(transport), uid, int(py))

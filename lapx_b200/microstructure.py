@@ -50,6 +50,39 @@ def voronoi(lib, grid, ngrains: int, seed: int = 0, z0: int = 0, nzl: int | None
     return ids, rot
 
 
+def voronoi_block(lib, grid, ngrains: int, seed: int, solver):
+    """Grain ids of the local block of `solver` (slab or pencil) and the per-grain rotations."""
+    ids, rot = voronoi(lib, grid, ngrains, seed, z0=solver.z0, nzl=solver.nzl)
+    return np.ascontiguousarray(ids[:, solver.y0:solver.y0 + solver.nyl, :]), rot
+
+
+def write_txt(lib, path: str, grain: np.ndarray, phase, rot9: np.ndarray):
+    """Per-voxel text file "phi1 Phi phi2 i j k grain phase" (evp_write_microstructure_txt)."""
+    nz, ny, nx = grain.shape
+    g = Grid(nx, ny, nz, 1.0, 1.0, 1.0)
+    gr = np.ascontiguousarray(grain, np.int32)
+    ph = None if phase is None else np.ascontiguousarray(phase, np.int32)
+    r = np.ascontiguousarray(rot9, np.float64)
+    rc = lib.evp_write_microstructure_txt(str(path).encode(), C.byref(g), gr.ctypes.data_as(C.c_void_p),
+                                          None if ph is None else ph.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise OSError(f"evp_write_microstructure_txt({path}) failed: {rc}")
+
+
+def read_txt(lib, path: str, grid):
+    """Read a per-voxel text file for `grid` = (nx, ny, nz): (grain[z,y,x], phase[z,y,x], rot9[9,z,y,x])."""
+    nx, ny, nz = (int(v) for v in grid)
+    g = Grid(nx, ny, nz, 1.0, 1.0, 1.0)
+    grain = np.empty((nz, ny, nx), np.int32)
+    phase = np.empty((nz, ny, nx), np.int32)
+    rot9 = np.empty((9, nz, ny, nx), np.float64)
+    rc = lib.evp_read_microstructure_txt(str(path).encode(), C.byref(g), grain.ctypes.data_as(C.c_void_p),
+                                         phase.ctypes.data_as(C.c_void_p), rot9.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise OSError(f"evp_read_microstructure_txt({path}) failed: {rc} (missing file, index out of range, duplicate or missing voxels)")
+    return grain, phase, rot9
+
+
 def expand_rotations(grain: np.ndarray, grain_rot: np.ndarray) -> np.ndarray:
     """Per-voxel rotation field in the ABI layout [9][z][y][x] from per-grain matrices."""
     r = grain_rot.reshape(-1, 9)[grain.reshape(-1)]          # (nvox, 9)

@@ -20,7 +20,7 @@
 //   CUDA  : deviatoric/hydrostatic b-basis, crystal-frame Newton, LDL^T, vector form of
 //           Gamma:lambda fused in the z pass, shared-memory Stockham power-of-two FFT.
 //
-// Build: make -C oracle    (g++ -O3 -march=x86-64-v3 -fopenmp -shared -fPIC)
+// Build: make -C oracle    (g++ -O3 -march=native -fopenmp -shared -fPIC; the library is always built on the host that runs it)
 
 #include "../include/evpfft.h"
 
@@ -235,6 +235,8 @@ struct evp_solver {
   std::vector<double> rot, sig, e, epsp, edotp, crss, gacc, twinf, de, wrot;
   std::vector<int32_t> twinned;
   long long ntwinned = 0;
+  double facc = 0.0;             // F_acc: twin volume fraction accumulated over the history (never decreases)
+  long long last_unconverged = 0;
   double C0[36]{}, S0[36]{};
   bool have_micro = false, have_c0 = false, have_loading = false, in_incr = false;
   evp_ctrl ctrl{1e-6, 1e-6, 100, 1, 1e-6, 100, 0, 0};
@@ -563,9 +565,9 @@ void plastic_rate(const evp_solver *S, size_t v, const VoxelFrame &F, const doub
 void op_constitutive(evp_solver *S, evp_iter_report *rep) {
   const size_t N = S->N;
   double sum_ds = 0, sum_de = 0, ssum[6] = {0, 0, 0, 0, 0, 0};
-  long nit_sum = 0;
+  long nit_sum = 0, unconv = 0;
   int nit_max = 0, nonfinite = 0;
-#pragma omp parallel for schedule(static) reduction(+ : sum_ds, sum_de, nit_sum, nonfinite, ssum[:6]) reduction(max : nit_max)
+#pragma omp parallel for schedule(static) reduction(+ : sum_ds, sum_de, nit_sum, nonfinite, unconv, ssum[:6]) reduction(max : nit_max)
   for (size_t v = 0; v < N; ++v) {
     VoxelFrame F;
     voxel_frame(S, v, F);
@@ -577,6 +579,7 @@ void op_constitutive(evp_solver *S, evp_iter_report *rep) {
       s6[c] = so[c];
     }
     int it = 0;
+    bool done = false;
     for (; it < S->ctrl.newton_itmax;) {
       // F(s) = S0 (s - so) + Sx s + ep + dt edp(s) - e
       double edp[6], dedp[36], res[6], J[36], d[6], t1[6], t2[6];
@@ -586,13 +589,14 @@ void op_constitutive(evp_solver *S, evp_iter_report *rep) {
       mat6_vec(F.Ssample, s6, t2);
       for (int c = 0; c < 6; ++c) res[c] = -(t1[c] + t2[c] + ep6[c] + S->dt * edp[c] - e6[c]);
       for (int k = 0; k < 36; ++k) J[k] = S->S0[k] + F.Ssample[k] + S->dt * dedp[k];
-      if (!gauss_solve(6, J, res)) { nonfinite += 1; break; }
+      if (!gauss_solve(6, J, res)) { nonfinite += 1; done = true; break; }
       double dn = 0, sn = 0;
       for (int c = 0; c < 6; ++c) { s6[c] += res[c]; dn += res[c] * res[c]; sn += s6[c] * s6[c]; }
       ++it;
-      if (!(dn == dn) || !(sn == sn)) { nonfinite += 1; break; }
-      if (std::sqrt(dn) <= S->ctrl.tol_newton * std::sqrt(sn)) break;
+      if (!(dn == dn) || !(sn == sn)) { nonfinite += 1; done = true; break; }
+      if (std::sqrt(dn) <= S->ctrl.tol_newton * std::sqrt(sn)) { done = true; break; }
     }
+    if (!done) unconv += 1;   // newton_itmax exhausted: sigma is not the converged multiplier for this voxel
     // error norms (published definitions): |sig_new - lambda_old| and |eps(sig_new) - e|
     double edp[6], t2[6], ds = 0, de = 0;
     plastic_rate(S, v, F, s6, edp, nullptr);
@@ -626,7 +630,9 @@ void op_constitutive(evp_solver *S, evp_iter_report *rep) {
     rep->newton_max = nit_max;
     rep->newton_mean = (double)nit_sum / (double)N;
     rep->nonfinite = nonfinite;
+    rep->unconverged = unconv;
   }
+  S->last_unconverged = unconv;
 }
 
 // Row a7: macro strain correction for stress-controlled components,
@@ -655,7 +661,8 @@ void fill_report(evp_solver *S, evp_iter_report *rep) {
   rep->err_stress = S->last_err_s;
   rep->err_strain = S->last_err_e;
   for (int c = 0; c < 6; ++c) { rep->savg[c] = S->savg[c]; rep->emacro[c] = S->E[c]; }
-  rep->converged = (S->iter >= S->ctrl.itmin && S->last_err_s <= S->ctrl.tol_stress && S->last_err_e <= S->ctrl.tol_strain) ? 1 : 0;
+  rep->converged = (S->iter >= S->ctrl.itmin && S->last_err_s <= S->ctrl.tol_stress && S->last_err_e <= S->ctrl.tol_strain &&
+                    S->last_unconverged == 0) ? 1 : 0;
 }
 
 double voce_tau(const evp_phase &p, int m, double G) {
@@ -729,8 +736,22 @@ int evp_local_slab(evp_handle h, int32_t *z0, int32_t *nzl) {
   if (nzl) *nzl = h->nz;
   return EVP_OK;
 }
+int evp_local_block(evp_handle h, int32_t *y0, int32_t *nyl, int32_t *z0, int32_t *nzl) {
+  if (!h) return EVP_ERR_ARG;
+  if (y0) *y0 = 0;
+  if (nyl) *nyl = h->ny;
+  if (z0) *z0 = 0;
+  if (nzl) *nzl = h->nz;
+  return EVP_OK;
+}
 int evp_nsys_max(evp_handle h) { return h ? h->nsmax : EVP_ERR_ARG; }
-int evp_transport(evp_handle) { return 0; }
+int evp_transport(evp_handle) { return EVP_TRANSPORT_NCCL; }
+#ifndef EVP_ORACLE_BUILD
+#define EVP_ORACLE_BUILD "EVPORACLE:manual"
+#endif
+const char *evp_build_id(void) { return EVP_ORACLE_BUILD; }
+int64_t evp_launch_count(evp_handle) { return 0; }
+int evp_debug_fp64_peak(evp_handle, int32_t, double *tflops) { if (tflops) *tflops = 0.0; return EVP_ERR_UNSUPPORTED; }
 
 int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *phase, const double *rot9) {
   if (!h || !grain || !rot9) return fail(h, EVP_ERR_ARG, "set_microstructure: null pointer");
@@ -746,7 +767,7 @@ int evp_set_microstructure(evp_handle h, const int32_t *grain, const int32_t *ph
   std::fill(h->epsp.begin(), h->epsp.end(), 0.0); std::fill(h->edotp.begin(), h->edotp.end(), 0.0);
   std::fill(h->gacc.begin(), h->gacc.end(), 0.0); std::fill(h->twinf.begin(), h->twinf.end(), 0.0);
   std::fill(h->de.begin(), h->de.end(), 0.0);
-  std::fill(h->wrot.begin(), h->wrot.end(), 0.0); std::fill(h->twinned.begin(), h->twinned.end(), 0); h->ntwinned = 0;
+  std::fill(h->wrot.begin(), h->wrot.end(), 0.0); std::fill(h->twinned.begin(), h->twinned.end(), 0); h->ntwinned = 0; h->facc = 0.0;
   for (size_t v = 0; v < N; ++v) {
     const PhaseData &pd = h->ph[h->phase[v]];
     for (int s = 0; s < h->nsmax; ++s)
@@ -871,8 +892,8 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (tex) local_rotation(h, wnew);
   double wapp[3] = {0.5 * (h->udot[3 * 2 + 1] - h->udot[3 * 1 + 2]), 0.5 * (h->udot[3 * 0 + 2] - h->udot[3 * 2 + 0]),
                     0.5 * (h->udot[3 * 1 + 0] - h->udot[3 * 0 + 1])};
-  double epsum[6] = {0, 0, 0, 0, 0, 0}, fsum = 0;
-#pragma omp parallel for schedule(static) reduction(+ : epsum[:6], fsum)
+  double epsum[6] = {0, 0, 0, 0, 0, 0}, dfsum = 0;
+#pragma omp parallel for schedule(static) reduction(+ : epsum[:6], dfsum)
   for (size_t v = 0; v < N; ++v) {
     const PhaseData &pd = h->ph[h->phase[v]];
     VoxelFrame F;
@@ -911,8 +932,11 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
     if (twn) {  // twin volume fractions: df = dgamma / S_tw
       for (int s = 0; s < pd.in.nsys; ++s) {
         const int m = pd.in.mode[s];
-        if (pd.in.twin[m] && pd.in.twin_shear[m] > 0) h->twinf[(size_t)s * N + v] += gdv[s] * h->dt / pd.in.twin_shear[m];
-        if (pd.in.twin[m]) fsum += h->twinf[(size_t)s * N + v];
+        if (pd.in.twin[m] && pd.in.twin_shear[m] > 0) {
+          const double df = gdv[s] * h->dt / pd.in.twin_shear[m];   // reoriented voxels keep contributing: F_acc is a history sum
+          h->twinf[(size_t)s * N + v] += df;
+          dfsum += df;
+        }
       }
     }
     if (tex) {  // lattice spin = applied spin + local (FFT) spin - plastic spin
@@ -929,7 +953,8 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   }
   // PTR: a voxel whose predominant twin system exceeds thr1 + thr2 * F_eff / F_acc takes the twin orientation
   long long nre = 0;
-  const double Facc = fsum / (double)N, Feff = (double)h->ntwinned / (double)N;
+  if (twn) h->facc += dfsum / (double)N;   // Tome, Lebensohn, Kocks 1991: accumulated, never reduced by a reorientation
+  const double Facc = h->facc, Feff = (double)h->ntwinned / (double)N;
   if (twn) {
 #pragma omp parallel for schedule(static) reduction(+ : nre)
     for (size_t v = 0; v < N; ++v) {
@@ -971,7 +996,7 @@ int evp_end_increment(evp_handle h, evp_step_report *rep) {
   if (rep) {
     rep->iters = h->iter;
     rep->err_stress = h->last_err_s; rep->err_strain = h->last_err_e;
-    rep->converged = (h->last_err_s <= h->ctrl.tol_stress && h->last_err_e <= h->ctrl.tol_strain) ? 1 : 0;
+    rep->converged = (h->last_err_s <= h->ctrl.tol_stress && h->last_err_e <= h->ctrl.tol_strain && h->last_unconverged == 0) ? 1 : 0;
     for (int c = 0; c < 6; ++c) { rep->savg[c] = h->savg[c]; rep->emacro[c] = h->E[c]; rep->epavg[c] = epsum[c] / (double)N; }
     rep->twin_acc = Facc; rep->twin_eff = (double)h->ntwinned / (double)N; rep->reoriented = nre;
   }
@@ -1044,11 +1069,13 @@ int evp_get_macro(evp_handle h, double emacro[6], double savg[6]) {
 }
 
 
+// restart file format "EVPCKPT2", identical to the product library's (include/evpfft.h)
 struct CkptHeader {
   char magic[8];
-  int32_t nx, ny, nz, z0, nzl, nsmax, nranks, rank;
+  int32_t nx, ny, nz, y0, nyl, z0, nzl, nsmax, nranks, rank;
   double Et[6], Edot_prev[6];
   int64_t ntwinned;
+  double facc;
 };
 
 int evp_save_state(evp_handle h, const char *path) {
@@ -1056,10 +1083,11 @@ int evp_save_state(evp_handle h, const char *path) {
   std::FILE *f = std::fopen(path, "wb");
   if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot write ") + path);
   CkptHeader hd{};
-  std::memcpy(hd.magic, "EVPCKPT1", 8);
-  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.z0 = 0; hd.nzl = h->nz; hd.nsmax = h->nsmax; hd.nranks = 1; hd.rank = 0;
+  std::memcpy(hd.magic, "EVPCKPT2", 8);
+  hd.nx = h->nx; hd.ny = h->ny; hd.nz = h->nz; hd.y0 = 0; hd.nyl = h->ny; hd.z0 = 0; hd.nzl = h->nz; hd.nsmax = h->nsmax; hd.nranks = 1; hd.rank = 0;
   for (int c = 0; c < 6; ++c) { hd.Et[c] = h->Et[c]; hd.Edot_prev[c] = h->Edot_prev[c]; }
   hd.ntwinned = h->ntwinned;
+  hd.facc = h->facc;
   bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1;
   auto wr = [&](const void *p, size_t bytes) { ok = ok && std::fwrite(p, 1, bytes, f) == bytes; };
   const size_t N = h->N, ns = (size_t)std::max(h->nsmax, 1);
@@ -1075,9 +1103,17 @@ int evp_load_state(evp_handle h, const char *path) {
   std::FILE *f = std::fopen(path, "rb");
   if (!f) return fail(h, EVP_ERR_ARG, std::string("cannot read ") + path);
   CkptHeader hd{};
-  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT1", 8) == 0;
-  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nz || hd.nsmax != h->nsmax)) ok = false;
+  bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::memcmp(hd.magic, "EVPCKPT2", 8) == 0;
+  if (ok && (hd.nx != h->nx || hd.ny != h->ny || hd.nz != h->nz || hd.nzl != h->nz || hd.nyl != h->ny || hd.nsmax != h->nsmax)) ok = false;
   if (!ok) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint does not match this handle"); }
+  {
+    const size_t N = h->N, ns = (size_t)std::max(h->nsmax, 1);
+    const size_t need = sizeof(hd) + (size_t)8 * N * (6 + 6 + 6 + ns + 9 + 1 + ns + 3) + (size_t)4 * N * 3;
+    std::fseek(f, 0, SEEK_END);
+    const long have = std::ftell(f);
+    std::fseek(f, (long)sizeof(hd), SEEK_SET);
+    if (have < 0 || (size_t)have != need) { std::fclose(f); return fail(h, EVP_ERR_ARG, "checkpoint file is truncated or has trailing bytes"); }
+  }
   auto rd = [&](void *p, size_t bytes) { ok = ok && std::fread(p, 1, bytes, f) == bytes; };
   const size_t N = h->N, ns = (size_t)std::max(h->nsmax, 1);
   rd(h->sig.data(), 6 * N * 8); rd(h->e.data(), 6 * N * 8); rd(h->epsp.data(), 6 * N * 8); rd(h->crss.data(), ns * N * 8);
@@ -1087,6 +1123,7 @@ int evp_load_state(evp_handle h, const char *path) {
   if (!ok) return fail(h, EVP_ERR_ARG, "short read");
   for (int c = 0; c < 6; ++c) { h->Et[c] = hd.Et[c]; h->E[c] = hd.Et[c]; h->Edot_prev[c] = hd.Edot_prev[c]; h->dEpend[c] = 0; }
   h->ntwinned = hd.ntwinned;
+  h->facc = hd.facc;
   h->have_micro = true; h->in_incr = false;
   return EVP_OK;
 }
@@ -1111,6 +1148,18 @@ int evp_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
 #else
+  return 1;
+#endif
+}
+// n <= 0: every online core.  bench.py calls this so that a launcher's OMP_NUM_THREADS=1 (torchrun) does not
+// silently turn the CPU baseline into a single-core run.
+int evp_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
   return 1;
 #endif
 }

@@ -9,11 +9,11 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_phase(host, hcp: bool, kind: int = 0):
-    if kind == 2:
+    if kind in (2, 3):
         import sys
         sys.path.insert(0, GOLDEN)
-        from common_golden import twin_phase
-        return twin_phase(host)
+        from common_golden import twin_phase, twin_phase_ratio
+        return twin_phase(host) if kind == 2 else twin_phase_ratio(host)
     if hcp:
         return ms.hcp_phase(host, with_twin=1, nrate=10.0,
                             voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
@@ -39,8 +39,9 @@ def solver_from_golden(lib, host, g, c0="golden"):
     return s
 
 
-def run_golden_schedule(s, g, hook=None):
-    """Run the fixed iteration schedule of a golden file; returns the report table (same columns)."""
+def run_golden_schedule(s, g, hook=None, step_reports=None):
+    """Run the fixed iteration schedule of a golden file; returns the report table (same columns).
+    `step_reports`: optional list that receives the evp_step_report of every end_increment."""
     rows = []
     dt = float(g["dt"])
     for inc in range(int(g["nincs"])):
@@ -53,7 +54,9 @@ def run_golden_schedule(s, g, hook=None):
             if hook:
                 hook(s, inc, it, "const")
             rows.append([inc, it + 1, r.err_stress, r.err_strain, *r.savg, *r.emacro, r.newton_max, r.newton_mean])
-        s.end_increment()
+        sr = s.end_increment()
+        if step_reports is not None:
+            step_reports.append(sr)
         if hook:
             hook(s, inc, -1, "end")
     return np.array(rows)

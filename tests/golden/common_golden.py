@@ -9,3 +9,11 @@ def twin_phase(lib):
     ph.twin_thr1 = 5.0e-8
     ph.twin_thr2 = 1.0e-13
     return ph
+
+
+def twin_phase_ratio(lib):
+    """As twin_phase, with a PTR threshold that depends on F_eff / F_acc (golden hcp8_twin_ratio)."""
+    ph = twin_phase(lib)
+    ph.twin_thr1 = 4.0e-8
+    ph.twin_thr2 = 1.0e-12
+    return ph

@@ -8,8 +8,10 @@ are both checked against the files this script writes (tests/test_oracle_golden.
 tests/test_gpu_parity.py).
 
 Run (CPU only, a few seconds):   python tests/golden/gen_golden.py
-Needs the built product library only for its host helpers (Voronoi ids, FCC/HCP tables), which
-are inputs, not algorithm.
+Needs the built product library only for the Voronoi grain ids (an input, itself checked bit-exactly against
+oracle/voronoi_ref.py).  The slip / twin system tables are NOT taken from the product library: they are built here
+from Miller(-Bravais) indices (tests/golden/crystal_tables.py), so a wrong table in host_tables.cpp shows up as a
+golden mismatch.
 """
 import os
 import sys
@@ -21,6 +23,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from lapx_b200 import api, microstructure as ms  # noqa: E402
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import crystal_tables as ct  # noqa: E402
+
+VOCE_HCP = [[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]]
+
+
+def fcc_phase_np(gamma0=1.0, nrate=10.0, tau0=16.0, tau1=0.0, theta0=0.0, theta1=0.0):
+    b, n = ct.fcc_systems()
+    return ct.fill_phase(api.Phase(), b, n, np.zeros(12, int), ct.cubic_voigt(ms.CU_C11, ms.CU_C12, ms.CU_C44), gamma0=gamma0,
+                         nrate=nrate, tau0=[tau0], voce=[[tau1, theta0, theta1]])
+
+
+def hcp_phase_np(with_twin=1, nrate=10.0, tau0_mode=(20.0, 100.0, 160.0, 80.0), voce_mode=None, thr=(0.1, 0.5)):
+    b, n, mode = ct.hcp_systems(ms.ZR_COVERA, with_twin)
+    twin_modes = tuple(range(3, 3 + with_twin))
+    return ct.fill_phase(api.Phase(), b, n, mode, ct.hex_voigt(*ms.ZR_C5), twin_modes=twin_modes, nrate=nrate, tau0=tau0_mode,
+                         voce=voce_mode, shears={m: ct.twin_shear(ms.ZR_COVERA, m) for m in twin_modes}, thr=thr)
+
 
 VM = np.array([[0, 5, 4], [5, 1, 3], [4, 3, 2]])
 PAIRS = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
@@ -147,6 +166,7 @@ class NumpyEVP:
         self.wrot = np.zeros((self.N, 3))
         self.twinf = np.zeros((self.N, ns))
         self.twinned = np.zeros(self.N, bool)
+        self.facc = 0.0                       # accumulated twin fraction: history sum, never reduced by a reorientation
         self.tshear = np.array([phase.twin_shear[m] for m in mode])
         self.W = np.array([1, 1, 1, np.sqrt(2), np.sqrt(2), np.sqrt(2)])
 
@@ -310,8 +330,10 @@ class NumpyEVP:
         nre = 0
         if self.update_twinning:
             tw = self.twin & (self.tshear > 0)
-            self.twinf[:, tw] += gd[:, tw] * self.dt / self.tshear[tw]
-            Facc = self.twinf[:, self.twin].sum() / self.N
+            df = gd[:, tw] * self.dt / self.tshear[tw]
+            self.twinf[:, tw] += df
+            self.facc += df.sum() / self.N
+            Facc = self.facc
             Feff = self.twinned.sum() / self.N
         if self.update_texture:
             wnew = self.local_rotation()
@@ -359,12 +381,13 @@ def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs,
     nx, ny, nz = grid
     ids, grot = ms.voronoi(lib, grid, ngrains, seed)
     if phase is None:
-        phase = ms.fcc_phase(lib, gamma0=1.0, nrate=10.0, tau0=16.0, tau1=10.0, theta0=200.0, theta1=10.0)
+        phase = fcc_phase_np(gamma0=1.0, nrate=10.0, tau0=16.0, tau1=10.0, theta0=200.0, theta1=10.0)
     S = NumpyEVP(phase, ids, grot)
     S.update_texture, S.update_twinning = texture, twinning
     S.set_loading(loading)
     reports = []
     fields = {}
+    twin_hist = []
     for inc in range(nincs):
         S.begin_increment(dt)
         for it in range(iters_per_inc):
@@ -387,9 +410,12 @@ def make_case(lib, name, grid, ngrains, seed, loading, dt, iters_per_inc, nincs,
             fields[f"twinned_end_inc{inc}"] = S.twinned.reshape(nz, ny, nx).astype(np.int32)
             if twinning:
                 print("   inc", inc, "twin F_acc, F_eff, reoriented:", S.last_twin)
-    if slim:  # keep the fixture small: final stress and strain only
+                twin_hist.append(list(S.last_twin))
+    if slim:  # keep the fixture small: final stress and strain (+ final twin flags) only
         last = nincs - 1
-        fields = {k: v for k, v in fields.items() if k in (f"sig_end_inc{last}", f"e_end_inc{last}")}
+        fields = {k: v for k, v in fields.items() if k in (f"sig_end_inc{last}", f"e_end_inc{last}", f"twinned_end_inc{last}")}
+    if twin_hist:
+        fields["twin_history"] = np.array(twin_hist)      # per increment: F_acc, F_eff, voxels reoriented
     c0v = S.C0m / np.outer(S.W, S.W)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
     np.savez_compressed(
@@ -406,15 +432,20 @@ def main():
     make_case(lib, "fcc8_strain", (8, 8, 8), 6, 0, api.Loading.strain_rate(D), 2e-4, 12, 2)
     make_case(lib, "fcc_12x10x8_tension", (12, 10, 8), 9, 3, api.Loading.uniaxial_tension(1.0), 2e-4, 10, 2)
     make_case(lib, "fcc_16x8x32_tension", (16, 8, 32), 12, 5, api.Loading.uniaxial_tension(1.0), 2e-4, 8, 2, slim=True)
-    hcp = ms.hcp_phase(lib, with_twin=1, nrate=10.0,
-                       voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
+    hcp = hcp_phase_np(with_twin=1, nrate=10.0, voce_mode=VOCE_HCP)
     make_case(lib, "hcp8_compression", (8, 8, 8), 5, 7, api.Loading.strain_rate(-D), 2e-4, 10, 2, phase=hcp, hcp=True)
     make_case(lib, "fcc8_texture", (8, 8, 8), 6, 2, api.Loading.strain_rate(D + np.array([[0, 0.3, 0], [-0.3, 0, 0], [0, 0, 0]])), 5e-4, 8, 3,
               texture=True)
     # HCP with easy tensile twinning and low PTR thresholds so that voxels reorient within a few increments
-    from common_golden import twin_phase
-    make_case(lib, "hcp8_twin_texture", (8, 8, 8), 5, 11, api.Loading.strain_rate(D), 1e-3, 8, 4, phase=twin_phase(lib), hcp=True,
+    # (same numbers as common_golden.twin_phase, which builds the product-side input from the product's own tables)
+    twin = hcp_phase_np(with_twin=1, nrate=10.0, tau0_mode=(60.0, 120.0, 200.0, 25.0), voce_mode=VOCE_HCP, thr=(5.0e-8, 1.0e-13))
+    make_case(lib, "hcp8_twin_texture", (8, 8, 8), 5, 11, api.Loading.strain_rate(D), 1e-3, 8, 4, phase=twin, hcp=True,
               texture=True, twinning=True, phase_kind=2)
+    # PTR threshold that depends on F_eff / F_acc: with F_acc as the history sum voxels reorient in increments 2, 4, 6; with the
+    # current-fraction sum (the defect fixed in round 2) they would in increments 2 and 5 only: the accumulated fraction must be the history sum
+    twin2 = hcp_phase_np(with_twin=1, nrate=10.0, tau0_mode=(60.0, 120.0, 200.0, 25.0), voce_mode=VOCE_HCP, thr=(4.0e-8, 1.0e-12))
+    make_case(lib, "hcp8_twin_ratio", (8, 8, 8), 5, 11, api.Loading.strain_rate(D), 1e-3, 6, 6, phase=twin2, hcp=True,
+              texture=False, twinning=True, phase_kind=3, slim=True)
 
 
 if __name__ == "__main__":

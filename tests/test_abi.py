@@ -27,7 +27,7 @@ def test_header_lists_match_binding():
 def test_product_exports_every_symbol(product_lib):
     for s in header_symbols():
         assert hasattr(product_lib, s), s
-    assert product_lib.evp_abi_version() == 1
+    assert product_lib.evp_abi_version() == 2
     assert product_lib.evp_backend() == b"cuda-sm100a"
 
 
@@ -35,6 +35,22 @@ def test_oracle_exports_common_symbols(oracle_lib):
     for s in api.ABI_SYMBOLS_COMMON:
         assert hasattr(oracle_lib, s), s
     assert oracle_lib.evp_backend() == b"cpu-oracle"
+    assert oracle_lib.evp_abi_version() == 2
+
+
+def test_build_id_is_the_digest_of_the_sources_in_the_tree(product_lib):
+    """build() decides staleness by content: the digest embedded in the binary equals the digest of the sources next
+    to it (a stale prebuilt .so would fail here and be rebuilt by build_product())."""
+    from lapx_b200 import build
+    assert product_lib.evp_build_id().decode() == "EVPSRC:" + build.source_id()
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors of the ABI structs: sizes computed from the header's field lists (LP64)."""
+    assert C.sizeof(api.Dist) == 4 * 4 + 128 + 4 + 12
+    assert C.sizeof(api.IterReport) == 4 + 4 + 8 * 3 + 48 + 48 + 4 + 4 + 8
+    assert C.sizeof(api.Ctrl) == 8 + 8 + 4 + 4 + 8 + 4 + 4 + 4 + 4   # trailing pad to 8
+    assert C.sizeof(api.StepReport) == 4 + 4 + 16 + 48 * 3 + 8 * 3 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

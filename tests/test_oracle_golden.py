@@ -6,7 +6,8 @@ import pytest
 from common import load_golden, rel_err, run_golden_schedule, solver_from_golden
 from lapx_b200 import api
 
-CASES = ["fcc8_strain", "fcc_12x10x8_tension", "hcp8_compression", "fcc_16x8x32_tension", "fcc8_texture", "hcp8_twin_texture"]
+CASES = ["fcc8_strain", "fcc_12x10x8_tension", "hcp8_compression", "fcc_16x8x32_tension", "fcc8_texture", "hcp8_twin_texture",
+         "hcp8_twin_ratio"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -29,9 +30,17 @@ def test_oracle_matches_numpy_golden(name, oracle_lib, product_lib):
             seen[f"rot_end_inc{inc}"] = s.get_field(api.FIELD_ROTATION)
             seen[f"twinned_end_inc{inc}"] = s.get_field(api.FIELD_TWINNED)[0]
 
-    rows = run_golden_schedule(s, g, hook)
+    twin = []
+    rows = run_golden_schedule(s, g, hook, step_reports=twin)
     ref = g["reports"]
     assert rows.shape == ref.shape
+    if "twin_history" in g.files:
+        # PTR bookkeeping per increment: F_acc (history sum, monotone), F_eff, voxels reoriented (integer, exact)
+        th = g["twin_history"]
+        got = np.array([[r.twin_acc, r.twin_eff, r.reoriented] for r in twin])
+        assert np.array_equal(got[:, 2], th[:, 2])
+        assert rel_err(got[:, :2], th[:, :2]) < 1e-8
+        assert np.all(np.diff(got[:, 0]) >= 0.0)            # F_acc never decreases, also across a reorientation
     # iteration bookkeeping identical, Newton counts identical
     assert np.array_equal(rows[:, :2], ref[:, :2])
     assert np.array_equal(rows[:, 16], ref[:, 16])
