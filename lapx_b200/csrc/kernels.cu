@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace evp {
 
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ C
           tma::store5(&tout.m[p2p ? d : 0], sm + (zt * NY + y0) * C::TX, 2 * k0, y0 & ((1 << lg_nyl_out) - 1), z0 + zt, c, p2p ? 0 : d);
       }
     tma::commit();
-    if (p2p) tma::wait_all0(); else tma::wait_read0();
+    if (p2p == 1) tma::wait_all0(); else tma::wait_read0();
   }
 }
 
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::T, ZCfg<NZ>::MINB) k_zfused(const __
           tma::store5(&tz.m[i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, r);
       }
     tma::commit();
-    if (p2p) tma::wait_all0(); else tma::wait_read0();
+    if (p2p == 1) tma::wait_all0(); else tma::wait_read0();
   }
 }
 
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_
       }
     }
   }
-  if (tid == 0) { if (p2p) tma::wait_all0(); else tma::wait_read0(); }
+  if (tid == 0) { if (p2p == 1) tma::wait_all0(); else tma::wait_read0(); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1122,6 +1123,12 @@ __global__ void k_init_crss(Fields f, int nsmax) {
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 
+// peer-memory stores: 1 = a block waits until its stores have been performed at the peer (cp.async.bulk.wait_group 0),
+// 2 = only until shared memory has been read out (the kernel boundary and the cross-GPU barrier that follows order the writes)
+int p2p_wait_mode() {
+  static const int m = getenv("EVP_P2P_WAIT") ? (std::string(getenv("EVP_P2P_WAIT")) == "read" ? 2 : 1) : 1;
+  return m;
+}
 bool fft_size_supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
 
 // opt in to large dynamic shared memory (static + dynamic > 48 KB), once per kernel instantiation (the call is not free)
@@ -1179,10 +1186,10 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout
     dim3 grid((nxh + C::TX - 1) / C::TX, (nzc + C::ZT - 1) / C::ZT, 6);                               \
     if (inv) {                                                                                        \
       set_smem(C::smem, k_ypass<NY, true>);                                                           \
-      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? 1 : 0, tw); \
+      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_ypass<NY, false>);                                                          \
-      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? 1 : 0, tw); \
+      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(ny, Y_)
@@ -1191,7 +1198,7 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout
 
 void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p_, int lg_nzl, int lg_nzc, int zrun,
                    int nxh /* local kx columns */, int kx0, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw, cudaStream_t st) { g_launches += 1;
-  const int p2p = p2p_ ? 1 : 0;
+  const int p2p = p2p_ ? p2p_wait_mode() : 0;
   const double rx = 1.0 / (nx * dx), ry = 1.0 / (ny * dy), rz = 1.0 / (nz * dz);
   const double scale = 1.0 / ((double)nx * ny * nz);
   static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16

@@ -49,6 +49,55 @@ class SpecLayout:
         return (z // self.nzl) * self.dstride + c * self.cstride + (z % self.nzl) * self.zstride + yl * self.nxp
 
 
+class PencilLayout:
+    """Pencil decomposition on a py x pz process grid, rank = iy*pz + iz (numpy restatement of evp_create's layouts).
+
+    real space       rank (iy, iz) owns y in [iy*nyb, +nyb), z in [iz*nzl, +nzl), all x
+    x stage (K2 out) kx pieces grouped by the row rank that will own them:
+                         addr(c, row, k) = (k // kxl) * dx + c * cx + row * kxl + k % kxl,    row = zl*nyb + yb
+    y stage          [nzl][ny][kxl] at kx0 = iy*kxl; x-side view: rows grouped by source row rank (nyb rows each),
+                     z-side view: rows grouped by destination column rank (nyl = ny/pz rows each)
+    z stage          [nz][nyl][kxl] at (ky0 = iz*nyl, kx0): planes grouped by source column rank
+    Every stage holds 6 * nzl * ny * kxl complex elements per rank."""
+
+    def __init__(self, nx, ny, nz, py, pz, rank):
+        self.py, self.pz = py, pz
+        self.iy, self.iz = rank // pz, rank % pz
+        self.nxh = nx // 2 + 1
+        self.kxl = ((self.nxh + py - 1) // py + 7) // 8 * 8
+        self.kx0 = self.iy * self.kxl
+        self.nxv = max(0, min(self.kxl, self.nxh - self.kx0))
+        self.nyb, self.y0 = ny // py, self.iy * (ny // py)
+        self.nzl, self.z0 = nz // pz, self.iz * (nz // pz)
+        self.nyl, self.ky0 = ny // pz, self.iz * (ny // pz)
+        self.cx = self.nzl * self.nyb * self.kxl          # x-side: component stride, group stride = 6*cx
+        self.dx = 6 * self.cx
+        self.cz = self.nzl * self.nyl * self.kxl          # z-side
+        self.dz = 6 * self.cz
+        self.size = 6 * self.nzl * ny * self.kxl
+
+    def addr_x(self, c, row, k):
+        return (k // self.kxl) * self.dx + c * self.cx + row * self.kxl + k % self.kxl
+
+    def row_xside(self, c, zl, y):
+        """y stage, x-side view (what the row exchange delivers / what K5 writes)."""
+        return (y // self.nyb) * self.dx + c * self.cx + zl * self.nyb * self.kxl + (y % self.nyb) * self.kxl
+
+    def row_zside(self, c, zl, y):
+        """y stage, z-side view (what K3 writes / the column exchange back delivers)."""
+        return (y // self.nyl) * self.dz + c * self.cz + zl * self.nyl * self.kxl + (y % self.nyl) * self.kxl
+
+    def row_zstage(self, c, z, yl):
+        return (z // self.nzl) * self.dz + c * self.cz + (z % self.nzl) * self.nyl * self.kxl + yl * self.kxl
+
+    def row_group(self):
+        """Ranks of my row (same iz, iy = 0..py-1) in exchange order."""
+        return [j * self.pz + self.iz for j in range(self.py)]
+
+    def col_group(self):
+        return [self.iy * self.pz + j for j in range(self.pz)]
+
+
 def nccl_unique_id(lib, rank: int, broadcast_bytes) -> "C.Array":
     """Rank 0 asks the library for an ncclUniqueId; `broadcast_bytes(np.uint8[128]) -> np.uint8[128]` ships it."""
     buf = (C.c_uint8 * 128)()
