@@ -604,6 +604,221 @@ __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4 for nz = 512 (every multi-GPU bench configuration; 512^3 on one GPU): PERSISTENT, one block per SM, one 192 KB tile
+// (6 components x 4 kx x 512 z) whose COMPONENT slots are pipelined individually by TMA:
+//   * two compute groups of 256 threads (components 0-2 / 3-5), each transforming its components ONE AFTER THE OTHER with
+//     three radix-8 passes synchronised by a named barrier of the group only -> the groups drift apart between the two
+//     block-wide barriers around the Green stage, so the shared-memory phases of one overlap the fp64 phases of the other;
+//   * one producer warp per group: as soon as component c of tile n has been inverse-transformed (mbarrier `done[c]`), its
+//     slot is stored (locally or straight into the owning rank's way-back buffer over NVLink) and, once the store has read the
+//     slot out, reloaded with component c of tile n+1.  A group needs its components in the order it released them one tile
+//     earlier, so every load has about a third of a tile of slack: neither the loads nor the peer stores are on the critical
+//     path (the one-shot kernel it replaces waits for both: 1 block/SM, load -> compute -> store -> cp.async.bulk.wait_group).
+//   * first-pass stores are permuted per lane so that a quarter-warp covers all banks; the last-pass twiddles live in registers
+//     within a direction.
+//   18 warps: 5 on one scheduler -> 96 registers per thread.
+// ---------------------------------------------------------------------------------------------
+template <int NZ>
+struct Z3Cfg {
+  static constexpr int TX = 4;
+  static constexpr int TPC = TX * NZ / 8;            // threads per component: 8 points each
+  static constexpr int TC = 2 * TPC;                 // compute threads (two groups)
+  static constexpr int T = TC + 64;                  // + one producer warp per group
+  static constexpr int CS = NZ * TX;                 // elements per component slot
+  static constexpr size_t tile = (size_t)6 * CS * sizeof(double2);
+  static constexpr size_t smem = tile + 16 * sizeof(uint64_t);
+};
+
+namespace tma {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tma
+__device__ __forceinline__ void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// read-only load the compiler must not hoist out of a loop (the value would be spilled across the Green stage)
+__device__ __forceinline__ double2 ldg_here(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// 512-point Stockham FFT of one column (stride TX) by the 64 threads q = 0..63 that share it; `barid`: the group's barrier
+template <int NZ, int TX, int NT, bool INV>
+__device__ __forceinline__ void z3_fft(double2 *__restrict__ s, int q, const double2 *__restrict__ twp, const double2 *tw3, int barid) {
+  constexpr int M = NZ / 8;
+  double2 v[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
+  bar_named(barid, NT);
+  bfly8<INV>(v);
+  {
+    const bool odd = (q & 1) != 0;   // odd lanes store their outputs pairwise swapped: a quarter-warp then covers all 8 bank groups
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const double2 a = v[r], b = v[r ^ 1];
+      s[(q * 8 + (odd ? (r ^ 1) : r)) * TX] = odd ? b : a;
+    }
+  }
+  bar_named(barid, NT);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
+  bar_named(barid, NT);
+  {
+    const int k8 = 8 * (q & 7);       // pass 2 twiddles W^(8 r (q mod 8)): eight distinct rows per warp, L1 hits
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      const double2 w = __ldg(twp + ((r * k8) & (NZ - 1)));
+      v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
+    }
+  }
+  bfly8<INV>(v);
+  {
+    const int k = q & 7, base = (q - k) * 8 + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[(base + r * 8) * TX] = v[r];
+  }
+  bar_named(barid, NT);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
+  bar_named(barid, NT);
+#pragma unroll
+  for (int r = 1; r < 8; ++r) v[r] = INV ? cmulc(v[r], tw3[r]) : cmul(v[r], tw3[r]);
+  bfly8<INV>(v);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s[(q + r * M) * TX] = v[r];
+}
+
+template <int NZ>
+__global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
+                                                             int lg_nzl, int lg_nzc, int zc, int ky0, int kx0, int nx, int ny, double rx, double ry,
+                                                             double rz, double scale, int nkx, int ntiles, const double2 *__restrict__ twp) {
+  using C = Z3Cfg<NZ>;
+  static_assert(NZ == 512, "three radix-8 passes");
+  extern __shared__ __align__(128) double2 sm[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + 6 * C::CS);   // full[c]: component c of the current tile has landed
+  uint64_t *done = full + 6;                                        // done[c]: component c has been transformed back (TPC arrivals)
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      tma::mbar_init(&full[c], 1);
+      tma::mbar_init(&done[c], C::TPC);
+    }
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid >= C::TC) {
+    // ---- producer warp of group g: stores and loads of components 3g .. 3g+2 ----
+    if ((tid & 31) != 0) return;
+    const int g = (tid - C::TC) >> 5;
+    auto issue_load = [&](int tile, int c) {
+      const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+      tma::mbar_expect_tx(&full[c], (uint32_t)(C::CS * sizeof(double2)));
+#pragma unroll 1
+      for (int z0 = 0; z0 < NZ; z0 += zc)
+        tma::load5(sm + c * C::CS + z0 * C::TX, &tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], &full[c], 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c,
+                   z0 >> lg_nzl);
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles)
+      for (int h = 0; h < 3; ++h) issue_load(tile, 3 * g + h);
+    for (int n = 0; tile < ntiles; tile += gridDim.x, ++n) {
+      const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+      const bool more = tile + (int)gridDim.x < ntiles;
+#pragma unroll 1
+      for (int h = 0; h < 3; ++h) {
+        const int c = 3 * g + h;
+        tma::mbar_wait(&done[c], n & 1);
+#pragma unroll 1
+        for (int z0 = 0; z0 < NZ; z0 += zc) {
+          const int r = z0 >> lg_nzl, i = (z0 & ((1 << lg_nzl) - 1)) >> lg_nzc;
+          if (p2p)   // planes of rank r go straight into rank r's way-back buffer (peer mapping): the transpose is this store
+            tma::store5(&tzo.m[r * kMaxChunksP2P + i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, 0);
+          else
+            tma::store5(&tz.m[i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, r);
+        }
+        tma::commit();
+        if (more) {
+          tma::wait_read0();                 // the slot has been read out: it can take component c of the next tile
+          issue_load(tile + gridDim.x, c);
+        }
+      }
+    }
+    if (p2p == 1) tma::wait_all0(); else tma::wait_read0();
+    return;
+  }
+  // ---- compute groups ----
+  const int g = tid / C::TPC, t = tid % C::TPC;
+  const int col = t % C::TX, q = t / C::TX;          // q in [0, NZ/8)
+  const int nxh = nx / 2 + 1;
+  int n = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+    double2 tw3[8];                                   // pass 3 twiddles W^(r q): in registers across the three components of a
+                                                      // direction, re-read (L1) after the Green stage rather than spilled across it
+#pragma unroll
+    for (int r = 1; r < 8; ++r) tw3[r] = ldg_here(twp + ((r * q) & (NZ - 1)));
+    tw3[0] = make_double2(1.0, 0.0);
+#pragma unroll 1
+    for (int h = 0; h < 3; ++h) {
+      const int c = 3 * g + h;
+      tma::mbar_wait(&full[c], n & 1);
+      z3_fft<NZ, C::TX, C::TPC, false>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
+    }
+    bar_named(1, C::TC);
+    // Green operator per frequency (row a2)
+    {
+      const int ky = ky0 + yl;
+      const int fy = (ky <= ny / 2) ? ky : ky - ny;
+#pragma unroll 1
+      for (int idx = tid; idx < C::CS; idx += C::TC) {
+        const int cc = idx % C::TX, kz = idx / C::TX;
+        const int kx = kx0 + k0 + cc;
+        if (kx < nxh) {
+          const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
+          const double x = kx * rx, y = fy * ry, z = fz * rz;
+          const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
+          const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
+          double gg[6];
+          if (!nyq && !zero) green_G(c_green, x, y, z, scale, gg);
+          double2 l2[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) l2[a] = sm[a * C::CS + idx];
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            double lam[6], o[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) lam[a] = part ? l2[a].y : l2[a].x;
+            if (zero) {
+#pragma unroll
+              for (int a = 0; a < 6; ++a) o[a] = 0.0;
+            } else if (nyq) {
+              green_nyquist(c_green, scale, lam, o);
+            } else {
+              green_apply(gg, x, y, z, lam, o);
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { if (part) l2[a].y = o[a]; else l2[a].x = o[a]; }
+          }
+#pragma unroll
+          for (int a = 0; a < 6; ++a) sm[a * C::CS + idx] = l2[a];
+        }
+      }
+    }
+    bar_named(1, C::TC);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) tw3[r] = ldg_here(twp + ((r * q) & (NZ - 1)));
+#pragma unroll 1
+    for (int h = 0; h < 3; ++h) {
+      const int c = 3 * g + h;
+      z3_fft<NZ, C::TX, C::TPC, true>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
+      tma::fence_proxy_async();          // this thread's generic-proxy writes, before the producer's TMA store reads them
+      tma::mbar_arrive(&done[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: constitutive update (rows a4, a5, a6).  One thread per voxel, 128 threads per block.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCB = 128;
@@ -1204,6 +1419,15 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
   static const int zver = getenv("EVP_ZKERNEL") ? atoi(getenv("EVP_ZKERNEL")) : 2;   // 1 = one-shot kernel, 2 = persistent radix-16
   static const int znb = getenv("EVP_ZNB") ? atoi(getenv("EVP_ZNB")) : 2;            // persistent kernel: resident blocks per SM (1 or 2)
   const bool fwd_only = mode == 1;
+  if (mode == 0 && !one_shot && zver == 2 && nz == 512) {
+    using C = Z3Cfg<512>;
+    static int nsm3 = 0;
+    if (!nsm3) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm3, cudaDevAttrMultiProcessorCount, dev); }
+    const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
+    set_smem(C::smem, k_zfused3<512>);
+    k_zfused3<512><<<ntiles < nsm3 ? ntiles : nsm3, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+    return;
+  }
   if (mode == 0 && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }

@@ -30,9 +30,10 @@ def test_chunked_equals_unchunked(grid, hcp, product_lib, monkeypatch):
             assert rel_err(a, b) < 1e-12, chunks
 
 
-@pytest.mark.parametrize("grid", [(16, 16, 128), (32, 8, 256), (8, 64, 128)])
+@pytest.mark.parametrize("grid", [(16, 16, 128), (32, 8, 256), (8, 64, 128), (16, 16, 512), (64, 8, 512), (256, 64, 512)])
 def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
-    """k_zfused2 (persistent, double-buffered, radix-16) vs k_zfused (one tile per block, radix-8 passes)."""
+    """k_zfused2 (nz = 128 / 256: persistent, radix-16) and k_zfused3 (nz = 512: persistent, component slots pipelined by
+    producer warps; the last grid gives every block several tiles) vs k_zfused (one tile per block, radix-8 passes)."""
     outs = []
     for flags in (0, 4):
         s, ids, grot = make_polycrystal(product_lib, product_lib, grid, 12, seed=5)

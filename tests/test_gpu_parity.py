@@ -94,7 +94,7 @@ def test_forward_fft_matches_scipy(grid, product_lib):
 
 @pytest.mark.parametrize("grid,ng,hcp,mode", [((32, 32, 32), 50, False, "tension"), ((16, 32, 64), 30, True, "strain"),
                                                 ((64, 64, 64), 200, False, "psc"), ((128, 16, 32), 40, False, "tension"),
-                                                ((256, 8, 16), 20, True, "psc")])
+                                                ((256, 8, 16), 20, True, "psc"), ((16, 16, 512), 30, False, "tension")])
 def test_gpu_matches_oracle_fixed_iterations(grid, ng, hcp, mode, product_lib, oracle_lib):
     """Configs 1/2/3 of BASELINE.json at oracle-friendly iteration counts: identical iteration
     sequence on both sides, compared per iteration (SURVEY.md §5 parity hazard)."""
@@ -376,7 +376,7 @@ def test_contract_sizes_match_oracle(name, grid, ng, hcp, mode, twinning, produc
     loading = api.Loading.plane_strain_compression(1.0) if mode == "psc" else api.Loading.uniaxial_tension(1.0)
     gpu, orc = _pair(product_lib, oracle_lib, grid, ng, hcp, loading, 1e-9, 1e-9, twinning=twinning)
     assert np.array_equal(gpu.get_field(api.FIELD_GRAIN), orc.get_field(api.FIELD_GRAIN))
-    assert rel_err(gpu.get_reference_medium(), orc.get_reference_medium()) < 1e-12
+    assert rel_err(gpu.get_reference_medium(), orc.get_reference_medium()) < 1e-11     # 1.7e7-term sums in different orders
     gpu.begin_increment(2e-4)
     orc.begin_increment(2e-4)
     for it in range(3):
