@@ -607,15 +607,18 @@ __global__ void __launch_bounds__(NB == 1 ? Z2Cfg<NZ>::T : Z2Cfg<NZ>::T2, NB) k_
 // K4 for nz = 512 (every multi-GPU bench configuration; 512^3 on one GPU): PERSISTENT, one block per SM, one 192 KB tile
 // (6 components x 4 kx x 512 z) whose COMPONENT slots are pipelined individually by TMA:
 //   * two compute groups of 256 threads (components 0-2 / 3-5), each transforming its components ONE AFTER THE OTHER with
-//     three radix-8 passes synchronised by a named barrier of the group only -> the groups drift apart between the two
-//     block-wide barriers around the Green stage, so the shared-memory phases of one overlap the fp64 phases of the other;
+//     three IN-PLACE radix-8 passes (decimation in frequency forward, in time backward; the Green stage works on the
+//     digit-reversed spectrum): a thread reads and writes the same elements, so a component direction needs ONE barrier of
+//     the group and one __syncwarp, and the warps run through load / butterfly / store phases unsynchronised — the
+//     shared-memory phases of some warps overlap the fp64 phases of others (ncu on the Stockham version of this kernel, which
+//     needed five group barriers per component direction: issue slots 34 % busy, shared memory 48 %, fp64 30 %);
+//   * rows z and z^1 are kept swapped where bit 3 of z is set between the first and the last pass of a direction, which makes all
+//     three passes bank-conflict free on the dense TMA tile (z3_swap);
 //   * one producer warp per group: as soon as component c of tile n has been inverse-transformed (mbarrier `done[c]`), its
 //     slot is stored (locally or straight into the owning rank's way-back buffer over NVLink) and, once the store has read the
 //     slot out, reloaded with component c of tile n+1.  A group needs its components in the order it released them one tile
 //     earlier, so every load has about a third of a tile of slack: neither the loads nor the peer stores are on the critical
 //     path (the one-shot kernel it replaces waits for both: 1 block/SM, load -> compute -> store -> cp.async.bulk.wait_group).
-//   * first-pass stores are permuted per lane so that a quarter-warp covers all banks; the last-pass twiddles live in registers
-//     within a direction.
 //   18 warps: 5 on one scheduler -> 96 registers per thread.
 // ---------------------------------------------------------------------------------------------
 template <int NZ>
@@ -642,50 +645,88 @@ __device__ __forceinline__ double2 ldg_here(const double2 *p) {
   return v;
 }
 
-// 512-point Stockham FFT of one column (stride TX) by the 64 threads q = 0..63 that share it; `barid`: the group's barrier
-template <int NZ, int TX, int NT, bool INV>
-__device__ __forceinline__ void z3_fft(double2 *__restrict__ s, int q, const double2 *__restrict__ twp, const double2 *tw3, int barid) {
-  constexpr int M = NZ / 8;
+// 512-point FFT of one column IN PLACE: decimation in frequency forward (natural order in, base-8 digit-reversed order out:
+// frequency 64c + 8b + a ends at position 64a + 8b + c) and decimation in time backward (digit-reversed in, natural out).
+// A thread reads and writes the same eight elements in every pass, so no barrier separates the loads from the stores of a pass:
+//   stride 64 (thread u = q)            <- group barrier ->   stride 8 (thread u: block u/8, j = u%8)   <- __syncwarp ->   stride 1
+// (the 32 lanes of a warp own one block of 64 points x 4 columns in the last two passes).
+// Bank conflicts: the tile is dense [z][4 kx] (64-byte rows, written by TMA).  In the stride-1 pass the lanes of a quarter-warp
+// belong to two threads u whose rows are 512 bytes apart: same banks.  Between the first pass and the last the rows z and z^1 are
+// therefore stored SWAPPED wherever bit 3 of z is set (position z' = z ^ ((z >> 3) & 1)): odd u then touch the other half of the
+// 128-byte bank row, and every pass is conflict free.  The first forward pass reads dense rows and writes swapped ones (the
+// target belongs to the neighbouring thread u^1 of the same warp: a __syncwarp orders it), the last inverse pass does the opposite.
+// tw64[r] = W^(r u) (stride-64 pass); the stride-8 twiddles W^(8 r (u%8)) are read from the table (eight rows per warp, L1).
+__device__ __forceinline__ int z3_swap(int z) { return z ^ ((z >> 3) & 1); }
+
+template <int NZ, int TX, int NT>
+__device__ __forceinline__ void z3_forward(double2 *__restrict__ s /* slot + col */, int u, const double2 *__restrict__ twp, const double2 *tw64, int barid) {
   double2 v[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
-  bar_named(barid, NT);
-  bfly8<INV>(v);
-  {
-    const bool odd = (q & 1) != 0;   // odd lanes store their outputs pairwise swapped: a quarter-warp then covers all 8 bank groups
+  for (int r = 0; r < 8; ++r) v[r] = s[(u + 64 * r) * TX];
+  bfly8<false>(v);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const double2 a = v[r], b = v[r ^ 1];
-      s[(q * 8 + (odd ? (r ^ 1) : r)) * TX] = odd ? b : a;
-    }
+  for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], tw64[r]);
+  __syncwarp();
+  {
+    const int us = z3_swap(u);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[(us + 64 * r) * TX] = v[r];
   }
   bar_named(barid, NT);
+  {
+    const int j = u & 7, base = (u >> 3) * 64 + j;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
+    for (int r = 0; r < 8; ++r) v[r] = s[((base + 8 * r) ^ (r & 1)) * TX];
+    bfly8<false>(v);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], __ldg(twp + 8 * j * r));
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[((base + 8 * r) ^ (r & 1)) * TX] = v[r];
+  }
+  __syncwarp();
+  {
+    const int o = u & 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = s[((8 * u + r) ^ o) * TX];
+    bfly8<false>(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[((8 * u + r) ^ o) * TX] = v[r];
+  }
+}
+template <int NZ, int TX, int NT>
+__device__ __forceinline__ void z3_inverse(double2 *__restrict__ s, int u, const double2 *__restrict__ twp, const double2 *tw64, int barid) {
+  double2 v[8];
+  {
+    const int o = u & 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = s[((8 * u + r) ^ o) * TX];
+    bfly8<true>(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[((8 * u + r) ^ o) * TX] = v[r];
+  }
+  __syncwarp();
+  {
+    const int j = u & 7, base = (u >> 3) * 64 + j;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = s[((base + 8 * r) ^ (r & 1)) * TX];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmulc(v[r], __ldg(twp + 8 * j * r));
+    bfly8<true>(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[((base + 8 * r) ^ (r & 1)) * TX] = v[r];
+  }
   bar_named(barid, NT);
   {
-    const int k8 = 8 * (q & 7);       // pass 2 twiddles W^(8 r (q mod 8)): eight distinct rows per warp, L1 hits
+    const int us = z3_swap(u);
 #pragma unroll
-    for (int r = 1; r < 8; ++r) {
-      const double2 w = __ldg(twp + ((r * k8) & (NZ - 1)));
-      v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
-    }
+    for (int r = 0; r < 8; ++r) v[r] = s[(us + 64 * r) * TX];
   }
-  bfly8<INV>(v);
-  {
-    const int k = q & 7, base = (q - k) * 8 + k;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) s[(base + r * 8) * TX] = v[r];
-  }
-  bar_named(barid, NT);
+  for (int r = 1; r < 8; ++r) v[r] = cmulc(v[r], tw64[r]);
+  bfly8<true>(v);
+  __syncwarp();
 #pragma unroll
-  for (int r = 0; r < 8; ++r) v[r] = s[(q + r * M) * TX];
-  bar_named(barid, NT);
-#pragma unroll
-  for (int r = 1; r < 8; ++r) v[r] = INV ? cmulc(v[r], tw3[r]) : cmul(v[r], tw3[r]);
-  bfly8<INV>(v);
-#pragma unroll
-  for (int r = 0; r < 8; ++r) s[(q + r * M) * TX] = v[r];
+  for (int r = 0; r < 8; ++r) s[(u + 64 * r) * TX] = v[r];
 }
 
 template <int NZ>
@@ -754,7 +795,7 @@ __global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_consta
   int n = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
     const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
-    double2 tw3[8];                                   // pass 3 twiddles W^(r q): in registers across the three components of a
+    double2 tw3[8];                                   // stride-64 twiddles W^(r q): in registers across the three components of a
                                                       // direction, re-read (L1) after the Green stage rather than spilled across it
 #pragma unroll
     for (int r = 1; r < 8; ++r) tw3[r] = ldg_here(twp + ((r * q) & (NZ - 1)));
@@ -763,7 +804,7 @@ __global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_consta
     for (int h = 0; h < 3; ++h) {
       const int c = 3 * g + h;
       tma::mbar_wait(&full[c], n & 1);
-      z3_fft<NZ, C::TX, C::TPC, false>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
+      z3_forward<NZ, C::TX, C::TPC>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
     }
     bar_named(1, C::TC);
     // Green operator per frequency (row a2)
@@ -772,7 +813,10 @@ __global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_consta
       const int fy = (ky <= ny / 2) ? ky : ky - ny;
 #pragma unroll 1
       for (int idx = tid; idx < C::CS; idx += C::TC) {
-        const int cc = idx % C::TX, kz = idx / C::TX;
+        // slot index -> (row, column) -> position (rows with bit 3 set are stored pairwise swapped) -> frequency (the forward
+        // transform leaves the spectrum in base-8 digit-reversed order)
+        const int cc = idx % C::TX, pos = z3_swap(idx / C::TX);
+        const int kz = ((pos & 7) << 6) | (pos & 0x38) | (pos >> 6);
         const int kx = kx0 + k0 + cc;
         if (kx < nxh) {
           const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
@@ -811,7 +855,7 @@ __global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_consta
 #pragma unroll 1
     for (int h = 0; h < 3; ++h) {
       const int c = 3 * g + h;
-      z3_fft<NZ, C::TX, C::TPC, true>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
+      z3_inverse<NZ, C::TX, C::TPC>(sm + c * C::CS + col, q, twp, tw3, 2 + g);
       tma::fence_proxy_async();          // this thread's generic-proxy writes, before the producer's TMA store reads them
       tma::mbar_arrive(&done[c]);
     }

@@ -169,7 +169,7 @@ int fail(evp_handle h, int code, const std::string &m) {
 int ilog2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 
 // 5-D tensor [2*nxp doubles][nyl][nzl][6][P] over a spectral buffer; box = [2*tx][box_y][box_z][1][1]
-bool make_tmap(CUtensorMap *m, void *base, const SpecLayout &L, int P, int tx, int box_y, int box_z, std::string *err) {
+bool make_tmap(CUtensorMap *m, void *base, const SpecLayout &L, int P, int tx, int box_y, int box_z, std::string *err, bool swizzle128 = false) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -185,7 +185,8 @@ bool make_tmap(CUtensorMap *m, void *base, const SpecLayout &L, int P, int tx, i
   const cuuint32_t box[5] = {(cuuint32_t)2 * tx, (cuuint32_t)box_y, (cuuint32_t)box_z, 1, 1};
   const cuuint32_t es[5] = {1, 1, 1, 1, 1};
   const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
     return false;
