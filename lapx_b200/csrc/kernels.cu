@@ -273,8 +273,8 @@ struct YCfg {
 // Tiles move by TMA: one op per (plane, chunk of yc rows); the split (all-to-all send) layout is the
 // 5-D tensor [kx][y % nyl][zl][c][y / nyl], the plain layout is the same with nyl = ny.
 template <int NY, bool INV>
-__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ CUtensorMap tin, const __grid_constant__ PeerMaps tout,
-                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out, int nzc, int p2p,
+__global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ PeerMaps tin, const __grid_constant__ PeerMaps tout,
+                                                       int lg_nyl_in, int yc_in, int lg_nyl_out, int yc_out, int nzc, int p2p, int pull,
                                                        const double2 *__restrict__ twp) {
   using C = YCfg<NY>;
   extern __shared__ __align__(128) double2 sm[];
@@ -292,8 +292,12 @@ __global__ void __launch_bounds__(YCfg<NY>::T) k_ypass(const __grid_constant__ C
   if (tid == 0) {
     tma::mbar_expect_tx(&bar, (uint32_t)(nzt * NY * C::TX * sizeof(double2)));
     for (int zt = 0; zt < nzt; ++zt)
-      for (int y0 = 0; y0 < NY; y0 += yc_in)
-        tma::load5(sm + (zt * NY + y0) * C::TX, &tin, &bar, 2 * k0, y0 & ((1 << lg_nyl_in) - 1), z0 + zt, c, y0 >> lg_nyl_in);
+      for (int y0 = 0; y0 < NY; y0 += yc_in) {
+        // pull: the rows that rank d transformed along z are read straight out of rank d's buffer over NVLink (TMA load on the
+        // peer mapping): the way-back FFT transpose is fused into this kernel's load phase.  Otherwise: local split / plain layout.
+        const int d = y0 >> lg_nyl_in;
+        tma::load5(sm + (zt * NY + y0) * C::TX, &tin.m[pull ? d : 0], &bar, 2 * k0, y0 & ((1 << lg_nyl_in) - 1), z0 + zt, c, pull ? 0 : d);
+      }
   }
   tma::mbar_wait(&bar, 0);
   const int l = tid % C::L, q = tid / C::L;
@@ -1437,7 +1441,7 @@ void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const Macr
 #undef X_
 }
 
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
+void launch_ypass(int ny, bool inv, const PeerMaps &tin, bool pull, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st) { g_launches += 1;
 #define Y_(NY)                                                                                        \
   {                                                                                                   \
@@ -1445,10 +1449,10 @@ void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout
     dim3 grid((nxh + C::TX - 1) / C::TX, (nzc + C::ZT - 1) / C::ZT, 6);                               \
     if (inv) {                                                                                        \
       set_smem(C::smem, k_ypass<NY, true>);                                                           \
-      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, tw); \
+      k_ypass<NY, true><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, pull ? 1 : 0, tw); \
     } else {                                                                                          \
       set_smem(C::smem, k_ypass<NY, false>);                                                          \
-      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, tw); \
+      k_ypass<NY, false><<<grid, C::T, C::smem, st>>>(tin, tout, in.lg, in.chunk, out.lg, out.chunk, nzc, p2p ? p2p_wait_mode() : 0, pull ? 1 : 0, tw); \
     }                                                                                                 \
   }
   EVP_DISPATCH_N(ny, Y_)

@@ -80,9 +80,11 @@ constexpr int kMaxChunks = 8;
 constexpr int kMaxRanks = 8;
 constexpr int kMaxChunksP2P = 4;   // pipeline chunks when the transposes are peer-memory stores (maps are kernel parameters)
 struct ZMaps { CUtensorMap m[kMaxChunks]; };   // one tensor map per pipeline chunk of the z-split buffer
-struct PeerMaps { CUtensorMap m[kMaxRanks]; }; // y pass output: m[0] = local send layout, or one map per destination rank (p2p)
+struct PeerMaps { CUtensorMap m[kMaxRanks]; }; // y pass input / output: m[0] = local layout, or one map per source / destination rank (peer memory)
 struct ZOutMaps { CUtensorMap m[kMaxRanks * kMaxChunksP2P]; };   // z pass output in p2p mode: [destination rank][chunk]
-void launch_ypass(int ny, bool inv, const CUtensorMap &tin, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
+// pull: input rows of source rank d are TMA-loaded from tin.m[d] (peer mapping);  p2p: output rows of destination rank d are
+// TMA-stored through tout.m[d]
+void launch_ypass(int ny, bool inv, const PeerMaps &tin, bool pull, const PeerMaps &tout, bool p2p, TileInfo in, TileInfo out, int nxh, int nzc,
                   const double2 *tw, cudaStream_t st);
 void launch_zfused(int nz, int mode /* 0 Green, 1 forward only, 2 local rotation */, bool one_shot, const ZMaps &tz, const ZOutMaps &tzo, bool p2p, int lg_nzl, int lg_nzc, int zrun,
                    int nxv /* local kx columns */, int kx0 /* first global kx */, int nyl, int ky0, int nx, int ny, double dx, double dy, double dz, const double2 *tw,

@@ -109,8 +109,12 @@ struct evp_solver {
     long long vbase = 0, count = 0;  // voxel range
     double2 *WA = nullptr, *WB = nullptr;
     CUtensorMap tm_y_plain{}, tm_y_split{};
+    PeerMaps in_fwd{};               // forward y pass input: m[0] = local plain layout
     PeerMaps out_fwd{};              // forward y pass output: m[0] = local send layout, or one map per destination rank (p2p)
+    PeerMaps in_inv{};               // inverse y pass input: m[0] = local split layout
+    PeerMaps in_pull{};              // inverse y pass input, p2p pull: one map per source rank (that rank's z-pass buffer)
     PeerMaps out_inv{};              // inverse y pass output: m[0] = local plain layout
+    cudaEvent_t ev_pull = nullptr;   // p2p pull: this chunk's inverse y pass (way-back transpose) has finished
     cudaEvent_t ev_fwd = nullptr, ev_a1 = nullptr, ev_a2 = nullptr;
     cudaEvent_t ev_p[4] = {nullptr, nullptr, nullptr, nullptr};   // pencil: kernel -> exchange hand-offs
     cudaEvent_t ev_q[2] = {nullptr, nullptr};                     // pencil: row exchanges done (way back, forward)
@@ -128,6 +132,10 @@ struct evp_solver {
   void *comm_row = nullptr, *comm_col = nullptr;   // pencil: x<->y exchange among the py ranks of a row, y<->z among the pz of a column
   // peer-memory transport: the transposes are TMA stores into the other ranks' buffers (CUDA IPC mappings)
   bool p2p = false;
+  bool pull = false;                 // p2p: way back = TMA loads from the peers' z-pass buffers in the inverse y pass (default), instead
+                                     // of TMA stores into the peers' way-back buffers in the z pass (EVP_WAYBACK=push)
+  cudaStream_t stp = nullptr;        // pull stream
+  cudaEvent_t ev_z = nullptr;
   double2 *WC = nullptr;             // p2p: receive buffer of the forward transpose (written by every rank's y pass)
   double2 *peerWA[kMaxRanks]{}, *peerWC[kMaxRanks]{};
   ZOutMaps zout{};
@@ -284,12 +292,12 @@ int enqueue_forward_chunk(evp_handle h, int i, const double *field = nullptr) {
     cudaEventRecord(c.ev_fwd, h->st);
     cudaStreamWaitEvent(h->stc, c.ev_fwd, 0);
     tbeg(h, 1, h->stc);
-    launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, true, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->stc);
+    launch_ypass(h->ny, false, c.in_fwd, false, c.out_fwd, true, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->stc);
     tend(h);
     return EVP_OK;
   }
   tbeg(h, 1, h->st);
-  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, false, c.in_fwd, false, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
   tend(h);
   if (h->nranks > 1) {
     cudaEventRecord(c.ev_fwd, h->st);
@@ -312,7 +320,7 @@ int enqueue_barrier(evp_handle h, void *comm, cudaStream_t st) {
 // K4 over all chunks (needs every forward exchange), then the way-back all-to-all of every chunk
 int enqueue_z_and_back(evp_handle h, int zmode = 0) {
   if (h->p2p) {
-    // all forward transposes (every rank's y-pass stores) done -> z pass, whose TMA stores ARE the way-back transpose
+    // all forward transposes (every rank's y-pass stores) done -> z pass
     tbeg(h, 6, h->stc);
     int rc = enqueue_barrier(h, h->comm, h->stc);
     tend(h);
@@ -320,12 +328,26 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
     cudaEventRecord(h->ev_b1, h->stc);
     cudaStreamWaitEvent(h->st, h->ev_b1, 0);
     tbeg(h, 2, h->st);
-    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, true, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
+    // pull: the z pass works in place on the receive buffer; push: its TMA stores ARE the way-back transpose
+    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, !h->pull, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
                   h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
     tend(h);
     tbeg(h, 6, h->st);
     rc = enqueue_barrier(h, h->comm2 ? h->comm2 : h->comm, h->st);
     tend(h);
+    if (rc == 0 && h->pull) {
+      // way back: the inverse y pass of every chunk TMA-loads its rows out of the peers' buffers, on the pull stream, so that
+      // the transpose of chunk i+1 runs under the x pass / Newton kernel of chunk i
+      cudaEventRecord(h->ev_z, h->st);
+      cudaStreamWaitEvent(h->stp, h->ev_z, 0);
+      for (int i = 0; i < h->nchunks; ++i) {
+        evp_solver::Chunk &c = h->ch[i];
+        tbeg(h, 3, h->stp);
+        launch_ypass(h->ny, true, c.in_pull, true, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->stp);
+        tend(h);
+        cudaEventRecord(c.ev_pull, h->stp);
+      }
+    }
     h->green_inflight = true;
     return rc;
   }
@@ -354,9 +376,13 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
 int enqueue_back_chunk(evp_handle h, int i, bool plain = false) {
   evp_solver::Chunk &c = h->ch[i];
   if (h->nranks > 1 && !h->p2p) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
-  tbeg(h, 3, h->st);
-  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
-  tend(h);
+  if (h->pull) {
+    cudaStreamWaitEvent(h->st, c.ev_pull, 0);     // K5 of this chunk ran on the pull stream (enqueue_z_and_back)
+  } else {
+    tbeg(h, 3, h->st);
+    launch_ypass(h->ny, true, c.in_inv, false, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
+    tend(h);
+  }
   tbeg(h, 4, h->st);
   launch_xinv(h->nx, c.WB, plain ? nullptr : h->f.e, (plain || (h->flags & 2)) ? h->f.de : nullptr, h->d_macro, h->N, c.rowbase,
               h->nyb * h->nzc, h->Lplain, h->twx, h->st);
@@ -392,7 +418,7 @@ int pencil_y_forward(evp_handle h, int i) {
   evp_solver::Chunk &c = h->ch[i];
   cudaStreamWaitEvent(h->st, c.ev_q[1], 0);
   tbeg(h, 1, h->st);
-  launch_ypass(h->ny, false, c.tm_y_plain, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, false, c.in_fwd, false, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->st);
   tend(h);
   cudaEventRecord(c.ev_p[1], h->st);
   cudaStreamWaitEvent(h->stc, c.ev_p[1], 0);
@@ -426,7 +452,7 @@ int pencil_y_back(evp_handle h, int i) {
   evp_solver::Chunk &c = h->ch[i];
   cudaStreamWaitEvent(h->st, c.ev_a2, 0);
   tbeg(h, 3, h->st);
-  launch_ypass(h->ny, true, c.tm_y_split, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
+  launch_ypass(h->ny, true, c.in_inv, false, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->st);
   tend(h);
   cudaEventRecord(c.ev_p[2], h->st);
   cudaStreamWaitEvent(h->stc, c.ev_p[2], 0);
@@ -480,6 +506,7 @@ int enqueue_reduce_macro(evp_handle h) {
 // the stress was changed from outside / buffers get reused: drop whatever transform is in flight
 void invalidate_green(evp_handle h) {
   if (h->green_inflight && h->stc) cudaStreamSynchronize(h->stc);
+  if (h->green_inflight && h->stp) cudaStreamSynchronize(h->stp);
   h->green_inflight = false;
 }
 
@@ -568,6 +595,7 @@ int fetch_report(evp_handle h, evp_iter_report *rep) {
   }
   if ((h->flags & 1) && h->tm.made) {
     if (h->stc) cudaStreamSynchronize(h->stc);
+    if (h->stp) cudaStreamSynchronize(h->stp);
     for (int i = 0; i < 8; ++i) h->last_ms[i] = 0;
     float ms;
     for (int i = 0; i < h->tm.n; ++i)
@@ -874,8 +902,10 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   }
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
+    S->pull = S->p2p && !(getenv("EVP_WAYBACK") && std::string(getenv("EVP_WAYBACK")) == "push");
     int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? 4 : 1);   // env: also on one rank (tests)
-    want = std::max(1, std::min(want, (int)(S->p2p ? kMaxChunksP2P : kMaxChunks)));
+    // push mode: the z pass carries one output tensor map per (destination, chunk) as kernel parameters
+    want = std::max(1, std::min(want, (int)((S->p2p && !S->pull) ? kMaxChunksP2P : kMaxChunks)));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->nyb * S->nx) % 128 != 0)) want /= 2;
     S->nchunks = want;
     S->nzc = S->nzl / want;
@@ -917,12 +947,18 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
                 make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, pz, zpass_tx(S->nz), 1, S->zrun, &e);
       for (int p = 0; p < kMaxRanks && ok; ++p) {
         c.out_inv.m[p] = c.tm_y_plain;
+        c.in_fwd.m[p] = c.tm_y_plain;
         c.out_fwd.m[p] = c.tm_y_split;
+        c.in_inv.m[p] = c.tm_y_split;
+        c.in_pull.m[p] = c.tm_y_split;
         if (S->p2p && p < nranks) {
+          // pull: the rows rank p transformed along z for my planes sit in p's receive buffer at source slot `rank`
+          ok = make_tmap(&c.in_pull.m[p], S->peerWC[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit, 1, ypass_tx(), ycs, 1, &e);
+          if (!ok) break;
           // my rows for destination p land in p's receive buffer at source slot `rank`
           ok = make_tmap(&c.out_fwd.m[p], S->peerWC[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit, 1, ypass_tx(), ycs, 1, &e);
           // my ky rows of p's planes land in p's way-back buffer at slot `rank`
-          if (ok) ok = make_tmap(&S->zout.m[p * kMaxChunksP2P + i], S->peerWA[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit,
+          if (ok && !S->pull) ok = make_tmap(&S->zout.m[p * kMaxChunksP2P + i], S->peerWA[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit,
                                  1, zpass_tx(S->nz), 1, S->zrun, &e);
         }
       }
@@ -934,6 +970,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
         CK(cudaEventCreateWithFlags(&c.ev_fwd, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_a1, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_a2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_pull, cudaEventDisableTiming));
         for (cudaEvent_t &ev : c.ev_p) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (cudaEvent_t &ev : c.ev_q) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       }
@@ -951,6 +988,8 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
         CK(cudaStreamCreateWithPriority(&S->stc, cudaStreamNonBlocking, pr));
       }
       CK(cudaEventCreateWithFlags(&S->ev_k4, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&S->ev_z, cudaEventDisableTiming));
+      CK(cudaStreamCreateWithFlags(&S->stp, cudaStreamNonBlocking));
     }
   }
   S->twx = make_twiddles(S->nx); S->twy = make_twiddles(S->ny); S->twz = make_twiddles(S->nz);
@@ -975,6 +1014,7 @@ int evp_destroy(evp_handle h) {
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->stc) cudaStreamSynchronize(h->stc);
+  if (h->stp) cudaStreamSynchronize(h->stp);
   if (h->p2p) {
     // the host synchronises the ranks before destroying handles (no collective here: a lone destroy must not hang);
     // every iteration ends with a cross-GPU barrier, so no peer store targets this rank once its own stream is idle
@@ -1005,12 +1045,15 @@ int evp_destroy(evp_handle h) {
     if (h->ch[i].ev_fwd) cudaEventDestroy(h->ch[i].ev_fwd);
     if (h->ch[i].ev_a1) cudaEventDestroy(h->ch[i].ev_a1);
     if (h->ch[i].ev_a2) cudaEventDestroy(h->ch[i].ev_a2);
+    if (h->ch[i].ev_pull) cudaEventDestroy(h->ch[i].ev_pull);
     for (cudaEvent_t ev : h->ch[i].ev_p) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ch[i].ev_q) if (ev) cudaEventDestroy(ev);
   }
   if (h->ev_k4) cudaEventDestroy(h->ev_k4);
   if (h->ev_it0) cudaEventDestroy(h->ev_it0);
   if (h->ev_it1) cudaEventDestroy(h->ev_it1);
+  if (h->ev_z) cudaEventDestroy(h->ev_z);
+  if (h->stp) cudaStreamDestroy(h->stp);
   if (h->stc) cudaStreamDestroy(h->stc);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
@@ -1554,7 +1597,7 @@ int evp_debug_spectrum(evp_handle h, int32_t comp, double *out) {
   activate(h);
   invalidate_green(h);
   launch_xfwd(h->nx, h->f.sig, h->WA, h->N, 0, h->ny * h->nzl, h->Lplain, h->twx, h->st);
-  launch_ypass(h->ny, false, h->ch[0].tm_y_plain, h->ch[0].out_inv, false, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
+  launch_ypass(h->ny, false, h->ch[0].in_fwd, false, h->ch[0].out_inv, false, h->ti_y_plain, h->ti_y_plain, h->nxh, h->nzl, h->twy, h->st);
   launch_zfused(h->nz, 1, true, h->zmaps, h->zout, false, h->lg_nzl, h->lg_nzc, h->zrun, h->nxh, 0, h->ny, 0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
   CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double2) * h->nxh, h->WA + (size_t)comp * h->Lplain.cstride, sizeof(double2) * h->nxp,
                                sizeof(double2) * h->nxh, (size_t)h->nz * h->ny, cudaMemcpyDeviceToHost, h->st));
