@@ -334,6 +334,58 @@ EVP_HD bool ldl6_solve_fast(double a[21], double b[6]) {
   return ok;
 }
 
+// LDL^T solve of a packed symmetric 5x5 (s5idx), pivot reciprocals by rcp_pivot
+EVP_HD bool ldl5_solve_fast(double a[15], double b[5]) {
+  double invd[5];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    double w[5];
+    double d = a[s5idx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      w[k] = a[s5idx(k, j)] * a[s5idx(k, k)];
+      d -= a[s5idx(k, j)] * w[k];
+    }
+    a[s5idx(j, j)] = d;
+    ok = ok && (d > 0.0);
+    const double inv = rcp_pivot(d);
+    invd[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 5; ++i) {
+      double t = a[s5idx(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= a[s5idx(k, i)] * w[k];
+      a[s5idx(j, i)] = t * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < 5; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) b[i] -= a[s5idx(k, i)] * b[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) b[i] *= invd[i];
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 5; ++k) b[i] -= a[s5idx(i, k)] * b[k];
+  }
+  return ok;
+}
+
+// Fast path: the plastic tangent lives in the deviatoric 5x5 block only, so the hydrostatic unknown s6 is eliminated once per
+// orientation class (block elimination is exact: the Newton iterates are those of the 6x6 solve):
+//   Jb = [K b; b^T d]   ->   table [K' = K - b b^T / d | b | d],     s6 = (g6 - b.s5)/d,     K' s5 + (1/n) A s5 = g5 - b g6 / d.
+// In place on the packed 6x6: entries (i,j<5) become K', (i,5) keep b, (5,5) keeps d.
+EVP_HD void jb_eliminate_hydrostatic(double Jb[21]) {
+  const double invd = 1.0 / Jb[sidx(5, 5)];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = i; j < 5; ++j) Jb[sidx(i, j)] -= Jb[sidx(i, 5)] * Jb[sidx(j, 5)] * invd;
+}
+
 // |x|^K for NQ values at once, level by level (independent chains side by side: instruction-level parallelism)
 template <int K, int NQ>
 EVP_HD void pow_ct_arr(const double (&x)[NQ], double (&r)[NQ]) {
@@ -476,6 +528,11 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
   static_assert(TAB != 2 || NS_T == 24, "HCP pattern: 24 systems");
   const double tol = cp.tol_newton;
   const int itmax = cp.newton_itmax;
+  // Jb is the eliminated table [K' | b | d]: g5 <- g5 - b g6/d once per voxel
+  const double invd = rcp_pivot(Jb(sidx(5, 5)));   // d = S0_c66 + S_c66 > 0: a compliance, never subnormal
+  const double g6d = g(5) * invd;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) g(i, g(i) - Jb(sidx(i, 5)) * g6d);
   int it = 0;
   bool conv = false;
   while (it < itmax) {
@@ -507,37 +564,39 @@ EVP_HD int newton_crystal_p(const PhaseDev &P, const ConstParams &cp, JB Jb, GV 
           for (int k = 0; k < 15; ++k) A[k] += w[q] * P.mm[q0 + q][k];
       }
     }
-    // F = g - Jb s - (1/n) A s ;  J = Jb + A
-    double J[21], F[6], As[5];
+    // 5x5 system of the deviatoric unknowns (hydrostatic one eliminated, jb_eliminate_hydrostatic):
+    //   F = g' - K' s5 - (1/n) A s5 ;  J = K' + A ;  g' was written over g(0..4) before the loop
+    double J[15], F[5], As[5];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) F[i] = g(i);
+    for (int i = 0; i < 5; ++i) { F[i] = g(i); As[i] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) As[i] = 0.0;
+    for (int i = 0; i < 5; ++i)
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i; j < 6; ++j) {
-        const double jb = Jb(sidx(i, j));
-        if (i < 5 && j < 5) {
-          const double a = A[s5idx(i, j)];
-          J[sidx(i, j)] = jb + a;
-          As[i] += a * s[j];
-          if (j != i) As[j] += a * s[i];
-        } else {
-          J[sidx(i, j)] = jb;
-        }
-        F[i] -= jb * s[j];
-        if (j != i) F[j] -= jb * s[i];
+      for (int j = i; j < 5; ++j) {
+        const double kp = Jb(sidx(i, j));
+        const double a = A[s5idx(i, j)];
+        J[s5idx(i, j)] = kp + a;
+        As[i] += a * s[j];
+        F[i] -= kp * s[j];
+        if (j != i) { As[j] += a * s[i]; F[j] -= kp * s[i]; }
       }
 #pragma unroll
     for (int i = 0; i < 5; ++i) F[i] -= cp.inv_n * As[i];
-    const bool ok = ldl6_solve_fast(J, F);
-    double dn = 0.0, sn = 0.0;
+    const bool ok = ldl5_solve_fast(J, F);
+    double dn = 0.0, sn = 0.0, bs = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 5; ++i) {
       s[i] += F[i];
       dn += F[i] * F[i];
       sn += s[i] * s[i];
+      bs += Jb(sidx(i, 5)) * s[i];
+    }
+    {
+      const double s6 = g6d - bs * invd;     // the linear hydrostatic equation holds exactly after every update
+      const double d6 = s6 - s[5];
+      s[5] = s6;
+      dn += d6 * d6;
+      sn += s6 * s6;
     }
     ++it;
     if (!ok || !(dn == dn) || !(sn == sn) || dn > 1e300 || sn > 1e300) { *bad = 1; conv = true; break; }
@@ -643,6 +702,52 @@ EVP_HD void constitutive_finish(const PhaseDev &P, MV M, const double sc[6], JB 
       acc[i] += w * d[j];
       if (j != i) acc[j] += w * d[i];
     }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) de2 += acc[a] * acc[a];
+  *ds = sqrt(ds2);
+  *de = sqrt(de2);
+  double sb[6];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double x = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) x += M(a * 5 + b) * sc[b];
+    sb[a] = x;
+  }
+  sb[5] = sc[5];
+  b_to_cart(sb, sig);
+}
+
+// constitutive_finish for the fast path: Jb is the eliminated table [K' | b | d] (jb_eliminate_hydrostatic), so the reference
+// compliance in the crystal frame is  S0_c = [K' + b b^T/d - Sc55 | b - Sc_b ; . | d - Sc66].
+template <class MV, class JB, class SV>
+EVP_HD void constitutive_finish_p(const PhaseDev &P, MV M, const double sc[6], JB Jb, SV sold, double sig[6], double *ds, double *de) {
+  double d[6], ds2 = 0.0, de2 = 0.0, acc[6], bd = 0.0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    d[a] = sc[a] - sold(a);
+    ds2 += d[a] * d[a];
+    acc[a] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) bd += Jb(sidx(i, 5)) * d[i];
+  const double dd = Jb(sidx(5, 5));
+  const double t = bd * rcp_pivot(dd) + d[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = i; j < 5; ++j) {
+      const double w = Jb(sidx(i, j)) - P.Sc[sidx(i, j)];
+      acc[i] += w * d[j];
+      if (j != i) acc[j] += w * d[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double b = Jb(sidx(i, 5));
+    acc[i] += b * t - P.Sc[sidx(i, 5)] * d[5];
+    acc[5] += (b - P.Sc[sidx(i, 5)]) * d[i];
+  }
+  acc[5] += (dd - P.Sc[sidx(5, 5)]) * d[5];
 #pragma unroll
   for (int a = 0; a < 6; ++a) de2 += acc[a] * acc[a];
   *ds = sqrt(ds2);

@@ -946,7 +946,7 @@ struct SmAcc {      // strided per-thread array in shared memory: element k of t
 
 // once per increment: orientation-dependent invariants (M, Jb) of every ORIENTATION CLASS and 1/tau_c of
 // every voxel.  Orientation classes are grains while the texture has not evolved per voxel, voxels after.
-__global__ void __launch_bounds__(kCB) k_prep_orient(Fields f) {
+__global__ void __launch_bounds__(kCB) k_prep_orient(Fields f, int fast) {
   const long long o = (long long)blockIdx.x * kCB + threadIdx.x;
   const long long NO = f.norient, N = f.N;
   if (o >= NO) return;
@@ -957,6 +957,7 @@ __global__ void __launch_bounds__(kCB) k_prep_orient(Fields f) {
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = f.rot[k * N + v];
   increment_invariants(P, c_cp, R, M, Jb);
+  if (fast) jb_eliminate_hydrostatic(Jb);   // fast path: table [K' | b | d] (5x5 Newton, evp_core.h)
 #pragma unroll
   for (int k = 0; k < 25; ++k) f.mrot[k * NO + o] = M[k];
 #pragma unroll
@@ -1145,7 +1146,7 @@ __global__ void __launch_bounds__(kCB, MINB) k_constitutive_p(Fields f, long lon
     double ds, de;
 #pragma unroll
     for (int k = 0; k < 25; ++k) M[k] = __ldg(f.mrot + k * NO + oid);   // second touch: L1/L2 hit
-    constitutive_finish(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
+    constitutive_finish_p(P, RegAcc25{M}, sc, jb, so, sig, &ds, &de);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       f.sig[c * N + v] = sig[c];
@@ -1613,7 +1614,7 @@ void launch_voxel_classes(const Fields &f, cudaStream_t st) { g_launches += 1; k
 
 void launch_prep_increment(const Fields &f, int nsmax, int fast_npow, cudaStream_t st) { g_launches += 2;
   const int nb = (int)((f.norient + kCB - 1) / kCB);
-  k_prep_orient<<<nb, kCB, 0, st>>>(f);
+  k_prep_orient<<<nb, kCB, 0, st>>>(f, fast_npow >= 0 ? 1 : 0);
   k_prep_itc<<<1184, 256, 0, st>>>(f, nsmax, fast_npow);
 }
 

@@ -125,6 +125,7 @@ struct evp_solver {
   SpecLayout Lplain{}, Lsplit{};     // per-chunk layouts (nzl := nzc)
   TileInfo ti_y_plain{}, ti_y_split{};
   int zrun = 0, lg_nzl = 0, lg_nzc = 0;
+  int zrun_z = 0, lg_nzc_z = 0;      // what the z pass sees: per-chunk sub-buffers, or (pull) one receive buffer for the whole slab
   cudaStream_t stc = nullptr;        // communication stream
   cudaEvent_t ev_k4 = nullptr, ev_it0 = nullptr, ev_it1 = nullptr;
   bool green_inflight = false;       // forward FFT + Green + way-back exchange of the CURRENT stress already enqueued
@@ -329,7 +330,7 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
     cudaStreamWaitEvent(h->st, h->ev_b1, 0);
     tbeg(h, 2, h->st);
     // pull: the z pass works in place on the receive buffer; push: its TMA stores ARE the way-back transpose
-    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, !h->pull, h->lg_nzl, h->lg_nzc, h->zrun, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
+    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, !h->pull, h->lg_nzl, h->lg_nzc_z, h->zrun_z, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
                   h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
     tend(h);
     tbeg(h, 6, h->st);
@@ -903,7 +904,9 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
     S->pull = S->p2p && !(getenv("EVP_WAYBACK") && std::string(getenv("EVP_WAYBACK")) == "push");
-    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? 4 : 1);   // env: also on one rank (tests)
+    // pull mode: the z pass does not see the chunks, and the exposed head (first pull) and tail (last push) of the pipeline shrink
+    // with the chunk size -> 8 chunks; otherwise 4
+    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? (S->pull ? 8 : 4) : 1);   // env: also on one rank (tests)
     // push mode: the z pass carries one output tensor map per (destination, chunk) as kernel parameters
     want = std::max(1, std::min(want, (int)((S->p2p && !S->pull) ? kMaxChunksP2P : kMaxChunks)));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->nyb * S->nx) % 128 != 0)) want /= 2;
@@ -943,8 +946,24 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
       // pencil (NCCL): K2 -> WA (x layout) -> [row a2a -> WB] -> K3 -> WA (split) -> [column a2a -> WB] -> K4 in place -> [column a2a -> WA]
       //                -> K5 -> WB (plain) -> [row a2a -> WA (x layout)] -> K6
       bool ok = make_tmap(&c.tm_y_plain, c.WB, S->Lplain, py, ypass_tx(), ycp, 1, &e) &&
-                make_tmap(&c.tm_y_split, c.WA, S->Lsplit, pz, ypass_tx(), ycs, 1, &e) &&
-                make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, pz, zpass_tx(S->nz), 1, S->zrun, &e);
+                make_tmap(&c.tm_y_split, c.WA, S->Lsplit, pz, ypass_tx(), ycs, 1, &e);
+      // pull mode: the receive buffer WC is laid out for the WHOLE slab ([source rank][c][z_local][ky_local][kx]); the chunks push
+      // into / pull from their own z range of it, and the z pass reads runs of up to 256 planes whatever the chunk count
+      SpecLayout Lwc = S->Lsplit;
+      Lwc.nzl = S->nzl; Lwc.lg_nzl = S->lg_nzl;
+      Lwc.cstride = (long long)S->nzl * Lwc.zstride;
+      Lwc.dstride = 6 * Lwc.cstride;
+      SpecLayout Lwc_chunk = Lwc;          // the same strides, the z extent of one chunk
+      Lwc_chunk.nzl = S->nzc;
+      const size_t zoff = (size_t)i * S->nzc * Lwc.zstride;
+      if (ok && S->pull) {
+        S->zrun_z = std::min(S->nzl, 256); S->lg_nzc_z = S->lg_nzl;
+        if (i == 0) ok = make_tmap(&S->zmaps.m[0], S->WC, Lwc, pz, zpass_tx(S->nz), 1, S->zrun_z, &e);
+        else S->zmaps.m[i] = S->zmaps.m[0];
+      } else if (ok) {
+        S->zrun_z = S->zrun; S->lg_nzc_z = S->lg_nzc;
+        ok = make_tmap(&S->zmaps.m[i], Wz, S->Lsplit, pz, zpass_tx(S->nz), 1, S->zrun, &e);
+      }
       for (int p = 0; p < kMaxRanks && ok; ++p) {
         c.out_inv.m[p] = c.tm_y_plain;
         c.in_fwd.m[p] = c.tm_y_plain;
@@ -953,8 +972,11 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
         c.in_pull.m[p] = c.tm_y_split;
         if (S->p2p && p < nranks) {
           // pull: the rows rank p transformed along z for my planes sit in p's receive buffer at source slot `rank`
-          ok = make_tmap(&c.in_pull.m[p], S->peerWC[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit, 1, ypass_tx(), ycs, 1, &e);
-          if (!ok) break;
+          if (S->pull) {
+            ok = make_tmap(&c.in_pull.m[p], S->peerWC[p] + (size_t)rank * Lwc.dstride + zoff, Lwc_chunk, 1, ypass_tx(), ycs, 1, &e) &&
+                 make_tmap(&c.out_fwd.m[p], S->peerWC[p] + (size_t)rank * Lwc.dstride + zoff, Lwc_chunk, 1, ypass_tx(), ycs, 1, &e);
+            continue;
+          }
           // my rows for destination p land in p's receive buffer at source slot `rank`
           ok = make_tmap(&c.out_fwd.m[p], S->peerWC[p] + (size_t)i * csize + (size_t)rank * S->Lsplit.dstride, S->Lsplit, 1, ypass_tx(), ycs, 1, &e);
           // my ky rows of p's planes land in p's way-back buffer at slot `rank`

@@ -67,9 +67,10 @@ int run_p(const PhaseDev &P, ConstParams &cp, const double *R, double *sig, cons
   double kn[EVP_MAX_SYS];
   for (int q = 0; q < NS_T; ++q) kn[q] = rate_factor(cp.dtg0n[q], 1.0 / itc[q], NPOW_T);   // k_prep_itc
   increment_invariants(P, cp, R, M, jb);
+  jb_eliminate_hydrostatic(jb);                                 // k_prep_orient, fast path
   constitutive_prep(cp, ArrAcc{M}, sig, em, ArrAcc{g}, ArrAcc{so}, sc);
   const int nit = newton_crystal_p<NS_T, NPOW_T, TWIN, G, TAB>(P, cp, ArrAcc{jb}, ArrAcc{g}, sc, ArrAcc{kn}, bad);
-  constitutive_finish(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
+  constitutive_finish_p(P, ArrAcc{M}, sc, ArrAcc{jb}, ArrAcc{so}, sig, ds, de);
   return nit;
 }
 }  // namespace
