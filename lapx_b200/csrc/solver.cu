@@ -135,9 +135,6 @@ struct evp_solver {
   bool p2p = false;
   bool pull = false;                 // p2p: way back = TMA loads from the peers' z-pass buffers in the inverse y pass (default), instead
                                      // of TMA stores into the peers' way-back buffers in the z pass (EVP_WAYBACK=push)
-  bool dma = false;                  // p2p: both transposes as copy-engine transfers between the peers' buffers (cudaMemcpyAsync on the IPC
-                                     // mappings): forward = push after the local y pass, way back = pull before the local inverse y pass.
-                                     // No SM waits on NVLink (EVP_WAYBACK=dma)
   cudaStream_t stp = nullptr;        // pull stream
   cudaEvent_t ev_z = nullptr;
   double2 *WC = nullptr;             // p2p: receive buffer of the forward transpose (written by every rank's y pass)
@@ -290,23 +287,6 @@ int enqueue_forward_chunk(evp_handle h, int i, const double *field = nullptr) {
   tbeg(h, 0, h->st);
   launch_xfwd(h->nx, field ? field : h->f.sig, c.WB, h->N, c.rowbase, nrows, h->Lplain, h->twx, h->st);
   tend(h);
-  if (h->dma) {
-    // local y pass into the send layout, then one copy-engine transfer per destination into that rank's receive buffer
-    cudaEventRecord(c.ev_fwd, h->st);
-    cudaStreamWaitEvent(h->stc, c.ev_fwd, 0);
-    tbeg(h, 1, h->stc);
-    launch_ypass(h->ny, false, c.in_fwd, false, c.out_fwd, false, h->ti_y_plain, h->ti_y_split, h->nxv, h->nzc, h->twy, h->stc);
-    tend(h);
-    const size_t piece = (size_t)h->Lsplit.dstride, csize = (size_t)6 * h->nzc * h->ny * h->nxp;
-    tbeg(h, 6, h->stc);
-    for (int k = 0; k < h->nranks; ++k) {
-      const int p = (h->rank + k) % h->nranks;     // every rank starts with a different destination
-      CUDA_OK(h, cudaMemcpyAsync(h->peerWC[p] + (size_t)i * csize + (size_t)h->rank * piece, c.WA + (size_t)p * piece, piece * sizeof(double2),
-                                 cudaMemcpyDeviceToDevice, h->stc));
-    }
-    tend(h);
-    return EVP_OK;
-  }
   if (h->p2p) {
     // y pass + forward transpose in one kernel (TMA stores into the peers' receive buffers), on the communication
     // stream: NVLink-bound, it runs under the constitutive kernel of the next chunk
@@ -350,32 +330,12 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
     cudaStreamWaitEvent(h->st, h->ev_b1, 0);
     tbeg(h, 2, h->st);
     // pull: the z pass works in place on the receive buffer; push: its TMA stores ARE the way-back transpose
-    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, !h->pull && !h->dma, h->lg_nzl, h->lg_nzc_z, h->zrun_z, h->nxv, h->kx0, h->nyl,
-                  h->ky0, h->nx, h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
+    launch_zfused(h->nz, zmode, (h->flags & 4) != 0, h->zmaps, h->zout, !h->pull, h->lg_nzl, h->lg_nzc_z, h->zrun_z, h->nxv, h->kx0, h->nyl, h->ky0, h->nx,
+                  h->ny, h->g.dx, h->g.dy, h->g.dz, h->twz, h->st);
     tend(h);
     tbeg(h, 6, h->st);
     rc = enqueue_barrier(h, h->comm2 ? h->comm2 : h->comm, h->st);
     tend(h);
-    if (rc == 0 && h->dma) {
-      // way back: per chunk, copy-engine pulls of my planes out of every peer's z-pass buffer, then the local inverse y pass
-      cudaEventRecord(h->ev_z, h->st);
-      cudaStreamWaitEvent(h->stp, h->ev_z, 0);
-      const size_t piece = (size_t)h->Lsplit.dstride, csize = (size_t)6 * h->nzc * h->ny * h->nxp;
-      for (int i = 0; i < h->nchunks; ++i) {
-        evp_solver::Chunk &c = h->ch[i];
-        tbeg(h, 6, h->stp);
-        for (int k = 0; k < h->nranks; ++k) {
-          const int p = (h->rank + k) % h->nranks;
-          CUDA_OK(h, cudaMemcpyAsync(c.WA + (size_t)p * piece, h->peerWC[p] + (size_t)i * csize + (size_t)h->rank * piece, piece * sizeof(double2),
-                                     cudaMemcpyDeviceToDevice, h->stp));
-        }
-        tend(h);
-        tbeg(h, 3, h->stp);
-        launch_ypass(h->ny, true, c.in_inv, false, c.out_inv, false, h->ti_y_split, h->ti_y_plain, h->nxv, h->nzc, h->twy, h->stp);
-        tend(h);
-        cudaEventRecord(c.ev_pull, h->stp);
-      }
-    }
     if (rc == 0 && h->pull) {
       // way back: the inverse y pass of every chunk TMA-loads its rows out of the peers' buffers, on the pull stream, so that
       // the transpose of chunk i+1 runs under the x pass / Newton kernel of chunk i
@@ -417,7 +377,7 @@ int enqueue_z_and_back(evp_handle h, int zmode = 0) {
 int enqueue_back_chunk(evp_handle h, int i, bool plain = false) {
   evp_solver::Chunk &c = h->ch[i];
   if (h->nranks > 1 && !h->p2p) cudaStreamWaitEvent(h->st, c.ev_a2, 0);
-  if (h->pull || h->dma) {
+  if (h->pull) {
     cudaStreamWaitEvent(h->st, c.ev_pull, 0);     // K5 of this chunk ran on the pull stream (enqueue_z_and_back)
   } else {
     tbeg(h, 3, h->st);
@@ -943,15 +903,10 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   }
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
-    {
-      const std::string wb = getenv("EVP_WAYBACK") ? getenv("EVP_WAYBACK") : "";
-      S->dma = S->p2p && wb == "dma";
-      S->pull = S->p2p && !S->dma && wb != "push";
-    }
-    // pull mode: the z pass does not see the chunks.  More chunks shorten the exposed head (first pull) and tail (last push) of
-    // the pipeline, but the transposes then time-share the SMs with the Newton kernel in smaller pieces; measured at 2 ranks
-    // (256x256x512): 2 / 4 / 8 chunks = 4.27 / 4.33 / 4.38 ms per iteration (profiles/r02_multigpu.md)
-    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? ((S->pull && nranks == 2) ? 2 : 4) : 1);   // env: also on one rank (tests)
+    S->pull = S->p2p && !(getenv("EVP_WAYBACK") && std::string(getenv("EVP_WAYBACK")) == "push");
+    // pull mode: the z pass does not see the chunks, and the exposed head (first pull) and tail (last push) of the pipeline shrink
+    // with the chunk size -> 8 chunks; otherwise 4
+    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? (S->pull ? 8 : 4) : 1);   // env: also on one rank (tests)
     // push mode: the z pass carries one output tensor map per (destination, chunk) as kernel parameters
     want = std::max(1, std::min(want, (int)((S->p2p && !S->pull) ? kMaxChunksP2P : kMaxChunks)));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->nyb * S->nx) % 128 != 0)) want /= 2;
@@ -1056,12 +1011,7 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
       }
       CK(cudaEventCreateWithFlags(&S->ev_k4, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&S->ev_z, cudaEventDisableTiming));
-      {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        const int mode = getenv("EVP_COMM_PRIO") ? atoi(getenv("EVP_COMM_PRIO")) : 0;
-        CK(cudaStreamCreateWithPriority(&S->stp, cudaStreamNonBlocking, (mode > 0) ? lo : (mode < 0 ? hi : 0)));
-      }
+      CK(cudaStreamCreateWithFlags(&S->stp, cudaStreamNonBlocking));
     }
   }
   S->twx = make_twiddles(S->nx); S->twy = make_twiddles(S->ny); S->twz = make_twiddles(S->nz);
