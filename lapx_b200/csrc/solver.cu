@@ -904,9 +904,11 @@ int evp_create(const evp_grid *grid, const evp_phase *phases, int32_t nphases, c
   // pipeline chunks: only with ranks > 1 (nothing to overlap otherwise); chunk voxel counts must be multiples of 128
   {
     S->pull = S->p2p && !(getenv("EVP_WAYBACK") && std::string(getenv("EVP_WAYBACK")) == "push");
-    // pull mode: the z pass does not see the chunks, and the exposed head (first pull) and tail (last push) of the pipeline shrink
-    // with the chunk size -> 8 chunks; otherwise 4
-    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? (S->pull ? 8 : 4) : 1);   // env: also on one rank (tests)
+    // pull mode: the z pass does not see the chunks.  More chunks shorten the exposed head (first pull) and tail (last push) of
+    // the pipeline, but the transposes then time-share the SMs with the Newton kernel in smaller pieces; measured at 2 ranks
+    // (256x256x512): 2 / 4 / 8 chunks = 4.27 / 4.33 / 4.38 ms per iteration (profiles/r02_multigpu.md).  With more ranks the
+    // transposes are longer (7/8 of the spectrum crosses NVLink at 8 ranks) and the head / tail weigh more: 4 chunks.
+    int want = getenv("EVP_CHUNKS") ? atoi(getenv("EVP_CHUNKS")) : ((nranks > 1) ? ((S->pull && nranks == 2) ? 2 : 4) : 1);   // env: also on one rank (tests)
     // push mode: the z pass carries one output tensor map per (destination, chunk) as kernel parameters
     want = std::max(1, std::min(want, (int)((S->p2p && !S->pull) ? kMaxChunksP2P : kMaxChunks)));
     while (want > 1 && (S->nzl % want != 0 || ((long long)(S->nzl / want) * S->nyb * S->nx) % 128 != 0)) want /= 2;
