@@ -463,12 +463,13 @@ def main():
     else:
         roof = {"kernel": KNAMES[dom], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": kern[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
-                "note": ("multi-rank: this kernel's TMA stores are the FFT transpose over NVLink; its time includes the exchange" if world > 1 and
-                         transport == "p2p" and KNAMES[dom] in ("z_fused", "y_fwd") else None)}
+                "note": ("multi-rank: this kernel's TMA stores / loads on peer memory are the FFT transpose over NVLink; its time includes the exchange"
+                         if world > 1 and transport == "p2p" and KNAMES[dom] in ("y_inv", "y_fwd") else None)}
     decomp = ("single GPU" if world == 1 else
               (f"{py} x {world // py} pencils, 4 NCCL all-to-alls per iteration on a communication stream" if py > 1 else
-               f"z-slabs over {world} GPUs, FFT transposes = " + ("TMA stores into peer memory (CUDA IPC over NVLink) fused into the y/z passes"
-                                                                  if transport == "p2p" else "NCCL all-to-all") + ", 4 pipelined z-chunks"))
+               f"z-slabs over {world} GPUs, FFT transposes = " + ("peer memory over NVLink (CUDA IPC): forward = TMA stores into the peers' receive buffers "
+                                                                  "fused into the forward y pass, way back = TMA loads out of the peers' z-pass buffers fused into "
+                                                                  "the inverse y pass" if transport == "p2p" else "NCCL all-to-all") + ", pipelined over z-chunks"))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

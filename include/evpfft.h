@@ -212,10 +212,15 @@ int  evp_set_field(evp_handle h, evp_field f, const void *host, size_t bytes);
 int  evp_get_macro(evp_handle h, double emacro[6], double savg[6]);
 
 /* ---- checkpoint / restart ------------------------------------------- */
-/* One raw binary file per rank: header (magic "EVPCKPT1", grid, slab, nsys_max), macroscopic state, then the state
- * fields in the ABI layout: stress, strain, plastic strain, CRSS, rotation, accumulated shear, twin fractions,
- * local rotation, grain, phase, twin flags.  evp_load_state needs a handle created with the same grid / phases /
- * decomposition and with the reference medium and loading already set.                                            */
+/* Restart file format "EVPCKPT2" — one raw little-endian binary file per rank, identical in both back ends:
+ *   header   char magic[8] = "EVPCKPT2"; int32 nx, ny, nz, y0, nyl, z0, nzl (local block), nsys_max, nranks, rank;
+ *            double Et[6] (macro strain at t), Edot_prev[6]; int64 ntwinned; double facc (accumulated twin fraction)
+ *   payload  the state fields of the local block in the ABI layout [component][z_local][y_local][x], in this order:
+ *            stress (6 fp64), strain (6), plastic strain (6), CRSS (ns), rotation (9), accumulated shear (1),
+ *            twin fractions (ns), local rotation (3), grain (int32), phase (int32), twin flags (int32);  ns = max(nsys_max, 1)
+ * The file size is checked against the header BEFORE any field is overwritten (a truncated file leaves the state untouched).
+ * evp_load_state needs a handle created with the same grid / phases / decomposition and with the reference medium and
+ * loading already set.                                                                                               */
 int  evp_save_state(evp_handle h, const char *path);
 int  evp_load_state(evp_handle h, const char *path);
 
