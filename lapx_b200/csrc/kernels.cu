@@ -1564,11 +1564,13 @@ static void launch_const_p(const Fields &f, long long vbase, long long count, do
 }
 
 // the uniform-exponent fast path (k_constitutive_p) applies to: one phase, every system with the same integer exponent
-// n in {10, 20}, and 12 systems without twins or 24 systems.  Returns n-1, or -1 when the generic kernels are used.
+// n in {10, 20}, and 12 systems without twins or 24 systems; n = 10 also with 30 systems.  Returns n-1, or -1 when the generic
+// kernels are used.
 int constitutive_fast_npow(int nphases, int uniform_ns, int uniform_npow, int any_twin) {
   const bool legacy = getenv("EVP_K1_LEGACY") && atoi(getenv("EVP_K1_LEGACY")) != 0;   // thread-loads kernel (A/B timing, tests)
   if (legacy || nphases != 1 || (uniform_npow != 9 && uniform_npow != 19)) return -1;
   if ((uniform_ns == 12 && !any_twin) || uniform_ns == 24) return uniform_npow;
+  if (uniform_ns == 30 && uniform_npow == 9) return uniform_npow;   // HCP with tensile + compressive twins (evp_phase_hcp, with_twin = 2)
   return -1;
 }
 
@@ -1594,6 +1596,7 @@ void launch_constitutive(const Fields &f, long long vbase, long long count, int 
       if (g_table == 2) return launch_const_p<24, 19, true, 3, 12, 2>(f, vbase, count, partials, st);
       return launch_const_p<24, 19, true, 3, 12>(f, vbase, count, partials, st);
     }
+    if (uniform_ns == 30) return launch_const_p<30, 9, true, 3, 10>(f, vbase, count, partials, st);   // 69 staged columns: 70 KB, 3 blocks per SM
   }
   if (one && uniform_ns == 12 && uniform_npow == 9) return launch_const_t<12, 9, true, 3>(f, vbase, count, nsmax, partials, st);
   if (one && uniform_ns == 12 && uniform_npow == 19) return launch_const_t<12, 19, true, 3>(f, vbase, count, nsmax, partials, st);

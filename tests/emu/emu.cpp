@@ -204,6 +204,7 @@ int emu_constitutive_t(int variant, const evp_phase *ph, const double *c0_voigt,
     case 13: return run_p<24, 9, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
     case 14: return run_p<12, 19, false, 6>(P, cp, R, sig, em, itc, ds, de, bad);
     case 15: return run_p<24, 19, true, 6>(P, cp, R, sig, em, itc, ds, de, bad);
+    case 20: return run_p<30, 9, true, 10>(P, cp, R, sig, em, itc, ds, de, bad);
     case 16: if (!fcc_table_matches(P)) return -1; return run_p<12, 9, false, 12, 1>(P, cp, R, sig, em, itc, ds, de, bad);
     case 17: if (!fcc_table_matches(P)) return -1; return run_p<12, 19, false, 12, 1>(P, cp, R, sig, em, itc, ds, de, bad);
     case 18: if (!hcp24_pattern_matches(P)) return -1; return run_p<24, 9, true, 12, 2>(P, cp, R, sig, em, itc, ds, de, bad);

@@ -48,7 +48,7 @@ def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
         assert rel_err(a, b) < 1e-11
 
 
-@pytest.mark.parametrize("hcp", [False, True])
+@pytest.mark.parametrize("hcp", [False, True, 2])
 def test_constitutive_kernel_variants_agree(hcp, product_lib, monkeypatch):
     """k_constitutive_p (bulk-staged fast path; FCC: compile-time Schmid table) vs the same kernel with run-time tables
     (EVP_K1_FCC=0) vs the thread-loads kernel k_constitutive_t (EVP_K1_LEGACY=1) vs the fast path without bulk staging
@@ -60,7 +60,11 @@ def test_constitutive_kernel_variants_agree(hcp, product_lib, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        s, ids, grot = make_polycrystal(product_lib, product_lib, (32, 16, 16), 12, seed=9, hcp=hcp)
+        ph = None
+        if hcp == 2:   # 30 systems: HCP with tensile and compressive twins (fast path vs the generic thread-loads kernel)
+            from lapx_b200 import microstructure as ms
+            ph = ms.hcp_phase(product_lib, with_twin=2, nrate=10.0, voce_mode=[[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]])
+        s, ids, grot = make_polycrystal(product_lib, product_lib, (32, 16, 16), 12, seed=9, hcp=bool(hcp), phase=ph)
         s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
         s.set_loading(api.Loading.uniaxial_tension(1.0))
         reps = []

@@ -128,12 +128,13 @@ def test_green_point_matches_tensor_formula(emu, product_lib):
 
 
 @pytest.mark.parametrize("hcp,nrate,variants", [(False, 10.0, [0, 1, 2, 11, 12, 16]), (True, 10.0, [0, 3, 6, 13, 18]), (False, 20.0, [0, 2, 4, 14, 17]),
-                                                 (True, 20.0, [5, 15, 19]), (False, 7.5, [0, 2])])
+                                                 (True, 20.0, [5, 15, 19]), (False, 7.5, [0, 2]), (2, 10.0, [0, 20])])
 @pytest.mark.parametrize("iso", [False, True])
 def test_constitutive_voxel_matches_sample_frame_newton(emu, product_lib, hcp, nrate, variants, iso):
     """Crystal-frame b-basis LDL^T Newton (kernel math) vs a sample-frame Mandel Newton in numpy."""
     rng = np.random.default_rng(11 + hcp + 2 * iso + int(nrate))
-    ph = ms.hcp_phase(product_lib, with_twin=1, nrate=nrate) if hcp else ms.fcc_phase(product_lib, nrate=nrate)
+    # hcp: True = 24 systems (tensile twins), 2 = 30 systems (+ compressive twins: the 30-system fast path, variant 20)
+    ph = ms.hcp_phase(product_lib, with_twin=int(hcp), nrate=nrate) if hcp else ms.fcc_phase(product_lib, nrate=nrate)
     if iso:
         K, mu = 140000.0, 48000.0
         c0 = np.zeros((6, 6))
