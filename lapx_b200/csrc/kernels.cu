@@ -867,6 +867,197 @@ __global__ void __launch_bounds__(Z3Cfg<NZ>::T, 1) k_zfused3(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4 for nz = 256, round-2 variant (k_zfused4, opt-in with EVP_Z4=1; not faster than k_zfused2, see launch_zfused): the design of
+// k_zfused3 on the 96 KB tile of nz = 256, two blocks per SM.
+//   * per block: three compute groups of 64 threads (group g transforms components g and g + 3, 16 points per thread) and one
+//     producer warp that stores / reloads every component slot as soon as its group has released it (k_zfused2 waits for the
+//     whole 96 KB tile after its last store: ncu, 23 % of the samples on that mbarrier);
+//   * IN-PLACE radix-16 passes: stride 16 with twiddles, then stride 1 (decimation in frequency; the spectrum is left in base-16
+//     digit-reversed order, frequency k1 + 16 k2 at position 16 k1 + k2, which the Green stage undoes), and the mirror image
+//     backward.  One barrier of the 64-thread group per component direction instead of four block barriers per pass pair;
+//   * rows z and z^1 are kept swapped where bit 4 of z is set between the first and the last pass (z4_swap): the stride-1 pass
+//     would otherwise hit every bank twice (two threads of a quarter-warp 1 KB apart).
+// ---------------------------------------------------------------------------------------------
+template <int NZ>
+struct Z4Cfg {
+  static constexpr int TX = 4;
+  static constexpr int TPC = TX * NZ / 16;           // 64 threads transform one component (16 points each)
+  static constexpr int NG = 3;                       // compute groups; group g owns components g and g + 3
+  static constexpr int TC = NG * TPC;                // 192 compute threads
+  static constexpr int T = TC + 32;                  // + one producer warp
+  static constexpr int CS = NZ * TX;
+  static constexpr size_t tile = (size_t)6 * CS * sizeof(double2);
+  static constexpr size_t smem = tile + 16 * sizeof(uint64_t);
+};
+__device__ __forceinline__ int z4_swap(int z) { return z ^ ((z >> 4) & 1); }
+__device__ __forceinline__ constexpr int z4_xr(int p) { return 4 * (p & 3) + (p >> 2); }   // bfly16 leaves X[z4_xr(p)] in v[p]
+
+template <int NZ, int TX, int NT>
+__device__ __forceinline__ void z4_forward(double2 *__restrict__ s /* slot + col */, int u, const double2 *__restrict__ twp, int barid) {
+  double2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = s[(u + 16 * r) * TX];
+  bfly16<false>(v);
+#pragma unroll
+  for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], __ldg(twp + u * z4_xr(p)));   // W_256^(u k1), k1 = z4_xr(p)
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 16; ++p) s[z4_swap(u + 16 * z4_xr(p)) * TX] = v[p];
+  bar_named(barid, NT);
+  {
+    const int o = u & 1;     // bit 4 of 16 u + r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = s[((16 * u + r) ^ o) * TX];
+    bfly16<false>(v);
+#pragma unroll
+    for (int p = 0; p < 16; ++p) s[((16 * u + z4_xr(p)) ^ o) * TX] = v[p];
+  }
+}
+template <int NZ, int TX, int NT>
+__device__ __forceinline__ void z4_inverse(double2 *__restrict__ s, int u, const double2 *__restrict__ twp, int barid) {
+  double2 v[16];
+  {
+    const int o = u & 1;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = s[((16 * u + r) ^ o) * TX];
+    bfly16<true>(v);
+#pragma unroll
+    for (int p = 0; p < 16; ++p) s[((16 * u + z4_xr(p)) ^ o) * TX] = v[p];
+  }
+  bar_named(barid, NT);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = s[z4_swap(u + 16 * r) * TX];
+#pragma unroll
+  for (int r = 1; r < 16; ++r) v[r] = cmulc(v[r], __ldg(twp + u * r));
+  bfly16<true>(v);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 16; ++p) s[(u + 16 * z4_xr(p)) * TX] = v[p];
+}
+
+template <int NZ>
+__global__ void __launch_bounds__(Z4Cfg<NZ>::T, 2) k_zfused4(const __grid_constant__ ZMaps tz, const __grid_constant__ ZOutMaps tzo, int p2p,
+                                                             int lg_nzl, int lg_nzc, int zc, int ky0, int kx0, int nx, int ny, double rx, double ry,
+                                                             double rz, double scale, int nkx, int ntiles, const double2 *__restrict__ twp) {
+  using C = Z4Cfg<NZ>;
+  static_assert(NZ == 256, "two radix-16 passes");
+  extern __shared__ __align__(128) double2 sm[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + 6 * C::CS);   // full[c]: component c of the current tile has landed
+  uint64_t *done = full + 6;                                        // done[c]: component c has been transformed back (TPC arrivals)
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      tma::mbar_init(&full[c], 1);
+      tma::mbar_init(&done[c], C::TPC);
+    }
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid >= C::TC) {
+    // ---- producer warp: stores and loads of all six component slots, in the order the groups release them ----
+    if ((tid & 31) != 0) return;
+    auto issue_load = [&](int tile, int c) {
+      const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+      tma::mbar_expect_tx(&full[c], (uint32_t)(C::CS * sizeof(double2)));
+#pragma unroll 1
+      for (int z0 = 0; z0 < NZ; z0 += zc)
+        tma::load5(sm + c * C::CS + z0 * C::TX, &tz.m[(z0 & ((1 << lg_nzl) - 1)) >> lg_nzc], &full[c], 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c,
+                   z0 >> lg_nzl);
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles)
+      for (int c = 0; c < 6; ++c) issue_load(tile, c);
+    for (int n = 0; tile < ntiles; tile += gridDim.x, ++n) {
+      const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+      const bool more = tile + (int)gridDim.x < ntiles;
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        tma::mbar_wait(&done[c], n & 1);
+#pragma unroll 1
+        for (int z0 = 0; z0 < NZ; z0 += zc) {
+          const int r = z0 >> lg_nzl, i = (z0 & ((1 << lg_nzl) - 1)) >> lg_nzc;
+          if (p2p)
+            tma::store5(&tzo.m[r * kMaxChunksP2P + i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, 0);
+          else
+            tma::store5(&tz.m[i], sm + c * C::CS + z0 * C::TX, 2 * k0, yl, z0 & ((1 << lg_nzc) - 1), c, r);
+        }
+        tma::commit();
+        if (more) {
+          tma::wait_read0();
+          issue_load(tile + gridDim.x, c);
+        }
+      }
+    }
+    if (p2p == 1) tma::wait_all0(); else tma::wait_read0();
+    return;
+  }
+  // ---- compute groups ----
+  const int g = tid / C::TPC, t = tid % C::TPC;
+  const int col = t % C::TX, u = t / C::TX;          // u in [0, 16)
+  const int nxh = nx / 2 + 1;
+  int n = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    const int k0 = (tile % nkx) * C::TX, yl = tile / nkx;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int c = g + 3 * h;
+      tma::mbar_wait(&full[c], n & 1);
+      z4_forward<NZ, C::TX, C::TPC>(sm + c * C::CS + col, u, twp, 2 + g);
+    }
+    bar_named(1, C::TC);
+    {
+      const int ky = ky0 + yl;
+      const int fy = (ky <= ny / 2) ? ky : ky - ny;
+#pragma unroll 1
+      for (int idx = tid; idx < C::CS; idx += C::TC) {
+        // slot index -> (row, column) -> position (rows with bit 4 set are stored pairwise swapped) -> frequency (base-16 digits reversed)
+        const int cc = idx % C::TX, pos = z4_swap(idx / C::TX);
+        const int kz = ((pos & 15) << 4) | (pos >> 4);
+        const int kx = kx0 + k0 + cc;
+        if (kx < nxh) {
+          const int fz = (kz <= NZ / 2) ? kz : kz - NZ;
+          const double x = kx * rx, y = fy * ry, z = fz * rz;
+          const bool zero = (kx == 0) && (ky == 0) && (kz == 0);
+          const bool nyq = (kx * 2 == nx) || (ky * 2 == ny) || (kz * 2 == NZ);
+          double gg[6];
+          if (!nyq && !zero) green_G(c_green, x, y, z, scale, gg);
+          double2 l2[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) l2[a] = sm[a * C::CS + idx];
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            double lam[6], o[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) lam[a] = part ? l2[a].y : l2[a].x;
+            if (zero) {
+#pragma unroll
+              for (int a = 0; a < 6; ++a) o[a] = 0.0;
+            } else if (nyq) {
+              green_nyquist(c_green, scale, lam, o);
+            } else {
+              green_apply(gg, x, y, z, lam, o);
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { if (part) l2[a].y = o[a]; else l2[a].x = o[a]; }
+          }
+#pragma unroll
+          for (int a = 0; a < 6; ++a) sm[a * C::CS + idx] = l2[a];
+        }
+      }
+    }
+    bar_named(1, C::TC);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int c = g + 3 * h;
+      z4_inverse<NZ, C::TX, C::TPC>(sm + c * C::CS + col, u, twp, 2 + g);
+      tma::fence_proxy_async();
+      tma::mbar_arrive(&done[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: constitutive update (rows a4, a5, a6).  One thread per voxel, 128 threads per block.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCB = 128;
@@ -1475,6 +1666,18 @@ void launch_zfused(int nz, int mode, bool one_shot, const ZMaps &tz, const ZOutM
     const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
     set_smem(C::smem, k_zfused3<512>);
     k_zfused3<512><<<ntiles < nsm3 ? ntiles : nsm3, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
+    return;
+  }
+  // nz = 256: EVP_Z4=1 selects k_zfused4 (in place, per-component TMA pipeline).  Measured 0.520 ms against 0.505 ms for k_zfused2 at
+  // 256^3 (same box, `profiles/r02_z4_{on,off}.json`): the second resident block already hides the tile load, so k_zfused2 stays the default
+  const int z4 = getenv("EVP_Z4") ? atoi(getenv("EVP_Z4")) : 0;
+  if (mode == 0 && !one_shot && zver == 2 && nz == 256 && z4) {
+    using C = Z4Cfg<256>;
+    static int nsm4 = 0;
+    if (!nsm4) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm4, cudaDevAttrMultiProcessorCount, dev); }
+    const int nkx = (nxh + C::TX - 1) / C::TX, ntiles = nkx * nyl;
+    set_smem(C::smem, k_zfused4<256>);
+    k_zfused4<256><<<ntiles < 2 * nsm4 ? ntiles : 2 * nsm4, C::T, C::smem, st>>>(tz, tzo, p2p, lg_nzl, lg_nzc, zrun, ky0, kx0, nx, ny, rx, ry, rz, scale, nkx, ntiles, tw);
     return;
   }
   if (mode == 0 && !one_shot && zver == 2 && (nz == 128 || nz == 256)) {

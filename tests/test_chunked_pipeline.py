@@ -30,12 +30,15 @@ def test_chunked_equals_unchunked(grid, hcp, product_lib, monkeypatch):
             assert rel_err(a, b) < 1e-12, chunks
 
 
-@pytest.mark.parametrize("grid", [(16, 16, 128), (32, 8, 256), (8, 64, 128), (16, 16, 512), (64, 8, 512), (256, 64, 512)])
-def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
-    """k_zfused2 (nz = 128 / 256: persistent, radix-16) and k_zfused3 (nz = 512: persistent, component slots pipelined by
-    producer warps; the last grid gives every block several tiles) vs k_zfused (one tile per block, radix-8 passes)."""
+@pytest.mark.parametrize("grid", [(16, 16, 128), (32, 8, 256), (8, 64, 128), (256, 64, 256), (16, 16, 512), (64, 8, 512), (256, 64, 512)])
+def test_persistent_z_kernel_equals_one_shot(grid, product_lib, monkeypatch):
+    """k_zfused2 (nz = 128: persistent, radix-16), k_zfused4 (nz = 256) and k_zfused3 (nz = 512) (persistent, in-place passes,
+    component slots pipelined by producer warps; the large grids give every block several tiles) vs k_zfused (one tile per
+    block, radix-8 Stockham passes)."""
     outs = []
-    for flags in (0, 4):
+    variants = [(0, "0"), (4, "0")] + ([(0, "1")] if grid[2] == 256 else [])      # nz = 256: also the opt-in k_zfused4
+    for flags, z4 in variants:
+        monkeypatch.setenv("EVP_Z4", z4)
         s, ids, grot = make_polycrystal(product_lib, product_lib, grid, 12, seed=5)
         s.set_profiling(flags)
         s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=10**6, tol_newton=1e-9, newton_itmax=100)
@@ -44,8 +47,9 @@ def test_persistent_z_kernel_equals_one_shot(grid, product_lib):
         for it in range(5):
             r = s.equilibrium_iter()
         outs.append((s.get_field(api.FIELD_STRESS), s.get_field(api.FIELD_STRAIN), np.array(r.savg[:])))
-    for a, b in zip(*outs):
-        assert rel_err(a, b) < 1e-11
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert rel_err(a, b) < 1e-11
 
 
 @pytest.mark.parametrize("hcp", [False, True, 2])
