@@ -401,6 +401,7 @@ def main():
     t_down = time.perf_counter() - t0
 
     if world > 1:
+        torch.cuda.synchronize()     # peers pull from / push into this rank's spectral buffers until its streams are idle
         td.barrier()
     transport = s.transport()
     s.close()
@@ -426,6 +427,7 @@ def main():
                                              "EVP uniaxial tension, mid-increment iterations", "grid": list(g4), "n_gpus": world, "scaling": "strong",
                                  "ms_per_step": ms4 / args.steps, "value": 256**3 * args.steps / (ms4 * 1e-3), "unit": UNIT,
                                  "newton_mean": r4.newton_mean, "transport": s4.transport()}
+        torch.cuda.synchronize()
         td.barrier()
         s4.close()
     if world > 1:

@@ -1777,11 +1777,13 @@ int constitutive_fast_npow(int nphases, int uniform_ns, int uniform_npow, int an
   return -1;
 }
 
+// fast_npow: the decision taken at evp_begin_increment (constitutive_fast_npow), which also fixed the form of the Jb tables and of
+// f.itc for this increment; it is not re-derived here, so the kernel always matches the tables it reads
 void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow,
-                         int any_twin, double *partials, cudaStream_t st) {
+                         int any_twin, int fast_npow, double *partials, cudaStream_t st) {
   const bool one = nphases == 1;
   static const int minb = getenv("EVP_K1_MINB") ? atoi(getenv("EVP_K1_MINB")) : 0;   // tuning knobs
-  if (constitutive_fast_npow(nphases, uniform_ns, uniform_npow, any_twin) >= 0) {
+  if (fast_npow >= 0) {
     if (uniform_ns == 12 && !any_twin) {
       if (uniform_npow == 9) {
         if (minb == 3) return launch_const_p<12, 9, false, 3, 12>(f, vbase, count, partials, st);

@@ -94,7 +94,7 @@ int zpass_tx(int nz);
 void launch_xinv(int nx, const double2 *W, double *e, double *de_dbg, const MacroDev *macro, long long N, int rowbase, int nrows,
                  SpecLayout L, const double2 *tw, cudaStream_t st);
 void launch_constitutive(const Fields &f, long long vbase, long long count, int nsmax, int nphases, int uniform_ns, int uniform_npow, int any_twin,
-                         double *partials, cudaStream_t st);
+                         int fast_npow /* decision of constitutive_fast_npow at evp_begin_increment */, double *partials, cudaStream_t st);
 void launch_reduce(const double *partials, long long N, double *scratch, double *totals, cudaStream_t st);
 long long partial_doubles(long long N);
 int reduce_scratch_doubles();

@@ -101,6 +101,7 @@ struct evp_solver {
   MacroDev *d_macro = nullptr, *h_macro = nullptr;  // h_macro pinned
   double *d_partials = nullptr, *d_totals = nullptr, *d_scratch = nullptr;
   int uniform_ns = 0, uniform_npow = -2;
+  int k1_fast = -1;       // >= 0: the uniform-exponent fast path runs this increment (set by evp_begin_increment)
   bool any_twin = false;
   // The local slab is processed in `nchunks` z-chunks of nzc planes, each with its own sub-buffers, so that with
   // ranks > 1 the all-to-alls of one chunk run (on the communication stream) under the kernels of the others.
@@ -487,7 +488,8 @@ int pencil_back_all(evp_handle h, bool plain) {
 
 void enqueue_const_chunk(evp_handle h, int i) {
   tbeg(h, 5, h->st);
-  launch_constitutive(h->f, h->ch[i].vbase, h->ch[i].count, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0, h->d_partials, h->st);
+  launch_constitutive(h->f, h->ch[i].vbase, h->ch[i].count, h->nsmax, h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0, h->k1_fast,
+                      h->d_partials, h->st);
   tend(h);
 }
 
@@ -1336,7 +1338,9 @@ int evp_begin_increment(evp_handle h, double dt) {
     m.E[c] = h->Et[c] + m.dEpend[c];
   }
   m.iter = 0;
-  launch_prep_increment(h->f, h->nsmax, constitutive_fast_npow(h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0), h->st);   // orientation / CRSS invariants of this increment
+  // which Newton kernel runs this increment (fast path or generic) fixes the form of the class tables and of f.itc: decided once, here
+  h->k1_fast = constitutive_fast_npow(h->nphases, h->uniform_ns, h->uniform_npow, h->any_twin ? 1 : 0);
+  launch_prep_increment(h->f, h->nsmax, h->k1_fast, h->st);   // orientation / CRSS invariants of this increment
   CUDA_OK(h, cudaMemcpyAsync(h->d_macro->E, m.E, sizeof(double) * 18, cudaMemcpyHostToDevice, h->st));  // E, Et, dEpend
   CUDA_OK(h, cudaMemcpyAsync(&h->d_macro->iter, &m.iter, sizeof(int), cudaMemcpyHostToDevice, h->st));
   CUDA_OK(h, cudaStreamSynchronize(h->st));

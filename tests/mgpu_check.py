@@ -49,7 +49,8 @@ def check_against_oracle(lib, td, world, rank, local, grid, ng, hcp, transport=a
     part, s = run(lib, lib, grid, ng, hcp, dd, niter=niter, nincs=nincs)
     tmp = tmp or os.environ.get("MGPU_TMP", tempfile.gettempdir())
     np.savez(os.path.join(tmp, f"mgpu_{rank}.npz"), **part)
-    td.barrier()          # files written; p2p transport: nobody frees a buffer a peer may still be writing to
+    torch.cuda.synchronize()   # this rank's own transposes (incl. the pulls already enqueued for a next iteration) have finished
+    td.barrier()               # files written; nobody frees a buffer a peer may still be reading or writing
     s.close()
     ok, info = True, None
     if rank == 0:
