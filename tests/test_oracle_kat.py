@@ -117,3 +117,77 @@ def test_green_operator_projector_identities(oracle_lib, product_lib):
     s.op_green()                    # e <- 0 - Gamma*(C0:eps) = -eps
     got = -s.get_field(api.FIELD_STRAIN)
     assert np.abs(got - eps).max() < 1e-12 * np.abs(eps).max()
+
+
+def _voce(ph, m, G):
+    t0, t1, h0, h1 = ph.tau0[m], ph.tau1[m], ph.theta0[m], ph.theta1[m]
+    return t0 + (t1 + h1 * G) * (1.0 - np.exp(-G * abs(h0 / t1)))
+
+
+@pytest.mark.parametrize("hcp", [False, True])
+def test_voce_hardening_follows_the_master_curve(hcp, oracle_lib, product_lib):
+    """Extended Voce with all latent coefficients equal to 1: whatever systems are active, d tau_s = [tau^(G + dG) - tau^(G)] * sum_s'
+    |d gamma_s'| / dG = tau^(G + dG) - tau^(G), so after every increment the CRSS of EVERY system of a voxel sits on the master
+    curve of its mode at that voxel's accumulated shear: crss_s(x) = tau^_mode(s)(Gamma(x)) (Tome et al. 1984)."""
+    voce = [[5.0, 100.0, 5.0], [10.0, 200.0, 10.0], [20.0, 400.0, 20.0], [5.0, 50.0, 5.0]]
+    ph = (ms.hcp_phase(product_lib, with_twin=1, nrate=10.0, voce_mode=voce) if hcp else
+          ms.fcc_phase(product_lib, nrate=10.0, tau0=16.0, tau1=10.0, theta0=200.0, theta1=10.0))
+    s, ids, grot = make_polycrystal(oracle_lib, product_lib, (8, 8, 8), 6, seed=3, phase=ph)
+    s.set_control(tol_stress=1e-6, tol_strain=1e-6, itmax=60, tol_newton=1e-10, newton_itmax=200)
+    s.set_loading(api.Loading.plane_strain_compression(1.0))
+    for inc in range(6):
+        s.step(5e-4)
+    crss, G = s.get_field(api.FIELD_CRSS), s.get_field(api.FIELD_GAMMA_ACC)[0]
+    assert G.min() > 0 and G.max() > 1e-4                     # plastic everywhere by now
+    for q in range(ph.nsys):
+        ref = _voce(ph, ph.mode[q], G)
+        assert np.abs(crss[q] - ref).max() < 1e-10 * ref.max(), q
+    assert crss.min() > min(ph.tau0[m] for m in range(ph.nmodes))          # it did harden
+
+
+def test_rate_sensitivity_saturation_stress(oracle_lib, product_lib):
+    """[001] tension of a cube-oriented FCC crystal without hardening: the flow stress saturates where the plastic strain rate equals
+    the imposed one, 8 m g0 (m s / tau)^n = rate with m = 1/sqrt 6, i.e. s_sat = (tau / m) (rate / (8 m g0))^(1/n); a ten times
+    faster test raises it by 10^(1/n)."""
+    n_exp, tau, g0, m = 10.0, 16.0, 1.0, 1 / np.sqrt(6)
+    sat = {}
+    for rate in (1.0, 10.0):
+        ph = ms.fcc_phase(product_lib, gamma0=g0, nrate=n_exp, tau0=tau)
+        s = api.Solver(oracle_lib, (8, 8, 8), [ph])
+        ids = np.zeros((8, 8, 8), np.int32)
+        s.set_microstructure(ids, None, ms.expand_rotations(ids, np.eye(3)[None]))
+        s.set_reference_medium(None)
+        s.set_control(tol_stress=1e-10, tol_strain=1e-10, itmax=200, tol_newton=1e-12, newton_itmax=200)
+        s.set_loading(api.Loading.uniaxial_tension(rate))
+        for inc in range(80):
+            rep = s.step(1e-4 / rate)                       # same strain per increment at both rates
+            assert rep.converged
+        sat[rate] = rep.savg[2]
+        analytic = (tau / m) * (rate / (8 * m * g0)) ** (1 / n_exp)
+        assert abs(sat[rate] - analytic) < 1e-6 * analytic, (rate, sat[rate], analytic)
+    assert abs(sat[10.0] / sat[1.0] - 10 ** (1 / n_exp)) < 1e-6
+
+
+def test_elastic_crystal_rotates_with_the_material_spin(oracle_lib, product_lib):
+    """Simple shear L12 = g of a single crystal that cannot slip (huge CRSS), texture update on: no plastic spin and no local (FFT)
+    spin, so the lattice follows the applied spin W = (L - L^T)/2, R(t) = exp(W t) R0: a rotation by -g t / 2 about x3."""
+    ph = ms.fcc_phase(product_lib, tau0=1e9)
+    s = api.Solver(oracle_lib, (8, 8, 8), [ph])
+    ids = np.zeros((8, 8, 8), np.int32)
+    rng = np.random.default_rng(1)
+    R0 = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    R0 *= np.sign(np.linalg.det(R0))
+    s.set_microstructure(ids, None, ms.expand_rotations(ids, R0[None]))
+    s.set_reference_medium(None)
+    s.set_control(tol_stress=1e-10, tol_strain=1e-10, itmax=100, tol_newton=1e-12, newton_itmax=100, update_texture=1)
+    g, dt, ninc = 0.8, 5e-3, 10
+    L = np.zeros((3, 3))
+    L[0, 1] = g
+    s.set_loading(api.Loading.strain_rate(L))
+    for inc in range(ninc):
+        s.step(dt)
+    th = -0.5 * g * dt * ninc
+    Q = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    rot = s.get_field(api.FIELD_ROTATION).reshape(9, -1)
+    assert np.abs(rot - (Q @ R0).reshape(9, 1)).max() < 1e-12
+    assert np.abs(s.get_field(api.FIELD_LOCAL_ROTATION)).max() < 1e-14
