@@ -191,3 +191,36 @@ def test_elastic_crystal_rotates_with_the_material_spin(oracle_lib, product_lib)
     rot = s.get_field(api.FIELD_ROTATION).reshape(9, -1)
     assert np.abs(rot - (Q @ R0).reshape(9, 1)).max() < 1e-12
     assert np.abs(s.get_field(api.FIELD_LOCAL_ROTATION)).max() < 1e-14
+
+
+def test_ptr_reorientation_is_the_85_degree_tensile_twin(oracle_lib, product_lib):
+    """PTR reorientation of a {10-12} tensile twin in Zr (c/a = 1.594): the voxel takes the twin orientation R (2 n n^T - I), a rotation
+    by 180 degrees about the twin-plane normal, which tilts the c axis by 2 atan((c/a)/sqrt 3) = 85.2 degrees (the textbook figure)."""
+    import sys
+    from common import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from common_golden import twin_phase
+    ph = twin_phase(product_lib)
+    grid = (8, 8, 8)
+    ids, grot = ms.voronoi(product_lib, grid, 5, 11)
+    s = api.Solver(oracle_lib, grid, [ph])
+    s.set_microstructure(ids, None, ms.expand_rotations(ids, grot))
+    s.set_reference_medium(None)
+    s.set_control(tol_stress=1e-30, tol_strain=1e-30, itmax=8, tol_newton=1e-9, newton_itmax=100, update_texture=0, update_twinning=1)
+    s.set_loading(api.Loading.strain_rate(np.diag([-0.5, -0.5, 1.0])))
+    r0 = s.get_field(api.FIELD_ROTATION).reshape(3, 3, -1)
+    total = 0
+    for inc in range(4):
+        total += s.step(1e-3).reoriented
+    tw = s.get_field(api.FIELD_TWINNED).reshape(-1).astype(bool)
+    assert total == tw.sum() >= 1
+    r1 = s.get_field(api.FIELD_ROTATION).reshape(3, 3, -1)
+    assert np.array_equal(r1[:, :, ~tw], r0[:, :, ~tw])                      # texture update off: only twinned voxels changed
+    c0, c1 = r0[:, 2, tw], r1[:, 2, tw]                                      # crystal c axis in the sample frame = third column of R
+    ang = np.degrees(np.arccos(np.clip(np.einsum("iv,iv->v", c0, c1), -1, 1)))
+    expect = np.degrees(2 * np.arctan(ms.ZR_COVERA / np.sqrt(3.0)))
+    assert abs(expect - 85.2) < 0.1
+    assert np.abs(ang - expect).max() < 1e-9
+    for v in np.where(tw)[0]:                                                # proper rotation by pi: Q = R0^T R1 symmetric, trace -1
+        Q = r0[:, :, v].T @ r1[:, :, v]
+        assert np.abs(Q - Q.T).max() < 1e-12 and abs(np.trace(Q) + 1) < 1e-12 and abs(np.linalg.det(Q) - 1) < 1e-12
